@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- CRF-loss fwd+bwd frames/s at 224^2 on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU path
+
+A step is one fwd+bwd of DenseCRFLoss over one batch of synthetic frames per GPU
+(configs[1] of BASELINE.json: 32 frames x 10 classes x 224x224, sigma_rgb=15, sigma_xy=100):
+lattice build + splat + blur + slice + loss reduction (forward) and the gradient kernel (backward).
+For N > 1 every rank runs the same per-GPU batch (weak scaling; 8 GPUs = configs[4]'s 256 frames)
+and the scalar loss is all-reduced over NCCL inside the timed region.
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "crf_loss_fwd_bwd_frames_per_sec_224"
+UNIT = "frames/s"
+H = W = 224
+SIGMA_RGB, SIGMA_XY = 15.0, 100.0
+D = 5
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--kind", choices=["noise", "natural"], default="noise")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (defeats L2 reuse)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 -> min(steps, 20)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# algorithmic bytes (restated in DESIGN.md "Roofline accounting")
+# ---------------------------------------------------------------------------
+def stage_bytes(P: int, d: int, K: int, M: float):
+    """Algorithmic bytes per FRAME of each pipeline stage; they sum to SURVEY §8(d)'s B_frame."""
+    dp1 = d + 1
+    return {
+        "build": 12 * P + 8 * dp1 * P,             # image in; offset + barycentric out
+        "neighbour": 8 * dp1 * M,                  # neighbour table out
+        "splat": 4 * K * P + 8 * dp1 * P + 4 * K * M,   # seg in; offset + bary in; value table out
+        "blur": dp1 * (8 * M + 16 * K * M),        # per axis: neighbour ids in, 3 values in, 1 value out
+        "slice": 8 * dp1 * P + 4 * K * M + 4 * K * P,   # offset + bary in; value table in; AS out
+        "loss": 0,
+        "backward": 4 * K * P,                     # gradient out
+    }
+
+
+def frame_bytes(P, d, K, M):
+    return float(sum(stage_bytes(P, d, K, M).values()))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.samples.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU reference timing (oracle/_ref when built, else the C port)
+# ---------------------------------------------------------------------------
+def cpu_fwd_bwd_frames_per_sec(frames: int, K: int, kind: str, reps: int, warmup: int = 1):
+    """Times the reference's CPU implementation of the same fwd+bwd on `frames` frames of the workload."""
+    import oracle
+    from tcam_wsol_video_b200 import synth
+
+    fn, which = oracle.best_filter(color=False)
+    img = synth.make_images(frames, H, W, kind, seed=0)
+    seg = synth.make_segs(frames, K, H, W, seed=0)
+    cores = len(os.sched_getaffinity(0))
+    if which == "reference":
+        threads = min(oracle.load_ref()[0].ref_omp_max_threads(), frames)
+    else:
+        threads = 1
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        oracle.densecrf_loss_fwd_bwd(img, seg, SIGMA_RGB, SIGMA_XY, 1.0, fn)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return frames / min(times), frames / (sum(times) / len(times)), which, threads, cores, times
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    frames = args.frames
+    t0 = time.perf_counter()
+    best, mean, which, threads, cores, times = cpu_fwd_bwd_frames_per_sec(frames, args.classes, args.kind,
+                                                                          reps=max(args.steps, 1),
+                                                                          warmup=max(args.warmup, 0))
+    value = frames * len(times) / sum(times)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": which, "host_cores": cores,
+                         "sample": f"{frames} frames x K={args.classes} x {H}x{W} ({args.kind}), fwd+bwd, "
+                                   f"{len(times)} steps, OpenMP over frames as shipped"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE configs[1]: DenseCRFLoss fwd+bwd, {args.frames} frames/GPU x {args.classes} classes x "
+                    f"{H}x{W} RGB, sigma_rgb={SIGMA_RGB:g}, sigma_xy={SIGMA_XY:g}, 5-D lattice, '{args.kind}' images",
+        "frames_per_gpu": args.frames, "classes": args.classes, "height": H, "width": W,
+        "image_kind": args.kind, "global_frames": args.frames * world,
+        "parallelism": f"dp{world} (frames sharded, scalar loss all-reduce)" if world > 1 else "single GPU",
+        "l2": f"{args.rotate} distinct input batches rotated; per-step working set (segs+AS+grad+tables) > 126 MB L2",
+    }
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    from tcam_wsol_video_b200 import _lib, ops, synth
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    assert lib.tcamcrf_device_count() >= 1
+
+    N, K = args.frames, args.classes
+    P = H * W
+    sets = []
+    for r in range(max(args.rotate, 1)):
+        seed = 1000 * rank + r
+        img = torch.from_numpy(synth.make_images(N, H, W, args.kind, seed=seed))
+        seg = torch.from_numpy(synth.make_segs(N, K, H, W, seed=seed))
+        sets.append((img.pin_memory(), seg.pin_memory(), img.to(dev), seg.to(dev).requires_grad_(True)))
+    crf = DenseCRFLoss(weight=2e-9, sigma_rgb=SIGMA_RGB, sigma_xy=SIGMA_XY, scale_factor=1.0).to(dev)
+
+    def step(i):
+        _, _, img_d, seg_d = sets[i % len(sets)]
+        seg_d.grad = None
+        loss = crf(images=img_d, segmentations=seg_d)
+        loss.backward()
+        if world > 1:
+            lv = loss.detach()
+            dist.all_reduce(lv)     # the path's only exchange: one scalar over NVLink
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # lattice size of this input (for the algorithmic-bytes formula)
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, SIGMA_RGB, SIGMA_XY)
+    _, _, ws = ops.crf_forward(sets[0][2], sets[0][3].detach(), cfg, check=True)
+    _, m_total = ops.workspace_status(ws)
+    M = m_total / N
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.tcamcrf_launch_count()
+    lib.tcamcrf_profile_enable(1)
+    lib.tcamcrf_profile_read(None, None, 1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    lib.tcamcrf_profile_enable(0)
+    st_ms = (ctypes.c_double * len(_lib.STAGES))()
+    st_ln = (ctypes.c_longlong * len(_lib.STAGES))()
+    lib.tcamcrf_profile_read(st_ms, st_ln, 1)
+    launches = lib.tcamcrf_launch_count() - launches0
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 20)
+        loss_h = torch.zeros(1).pin_memory()
+        grad_h = torch.empty(N, K, H, W).pin_memory()
+        cfg_h = _lib.make_config(_lib.FEAT_XY_RGB, 3, SIGMA_RGB, SIGMA_XY)
+
+        def e2e_step(i):
+            img_h, seg_h, _, _ = sets[i % len(sets)]
+            rc = lib.tcamcrf_loss_fwd_bwd_host(ctypes.byref(cfg_h), img_h.data_ptr(), seg_h.data_ptr(),
+                                               loss_h.data_ptr(), grad_h.data_ptr(), N, K, H, W, 2e-9)
+            _lib.check(rc, "tcamcrf_loss_fwd_bwd_host")
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": world * N * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(4 * N * 3 * P + 4 * N * K * P + 4),
+               "d2h_bytes_per_step": int(4 * N * K * P + 4 + 4),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "tcamcrf_loss_fwd_bwd_host (host pointers in, loss + gradient out)"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    sb = stage_bytes(P, D, K, M)
+    stages = {}
+    for i, name in enumerate(_lib.STAGES):
+        if st_ln[i] > 0:
+            per_launch_ms = st_ms[i] / st_ln[i]
+            launches_per_step = st_ln[i] / args.steps
+            bytes_per_launch = sb[name] * N / launches_per_step
+            stages[name] = {"ms_per_step": st_ms[i] / args.steps, "launches_per_step": launches_per_step,
+                            "ms_per_launch": per_launch_ms,
+                            "gbs": bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
+    dom = max(stages, key=lambda s: stages[s]["ms_per_step"]) if stages else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{dom}:{args.kind}:K{K}:N{N}")
+        except Exception:
+            traffic = None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": sb[dom] * N / stages[dom]["launches_per_step"],
+                    "ms_per_launch": stages[dom]["ms_per_launch"],
+                    "pipeline": {"bytes_per_frame": frame_bytes(P, D, K, M), "vertices_per_frame": M,
+                                 "achieved": frame_bytes(P, D, K, M) * value / world / 1e9,
+                                 "frac": frame_bytes(P, D, K, M) * value / world / 1e9 / peak},
+                    "stages": stages}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        frames = min(N, 32)
+        best, mean, which, threads, cores, times = cpu_fwd_bwd_frames_per_sec(frames, K, args.kind, reps=3, warmup=1)
+        cpu = {"value": best, "unit": UNIT, "cores": threads, "kind": which, "host_cores": cores,
+               "sample": f"{frames} frames x K={K} x {H}x{W} ({args.kind}), fwd+bwd, best of 3 after 1 warm-up, "
+                         f"OpenMP over frames as shipped", "mean_value": mean}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/*
+ * tcamcrf.h -- C ABI of libtcamcrf.so: the B200-native (sm_100a) DenseCRF-loss
+ * hot path of TCAM (permutohedral-lattice bilateral filter, loss, gradient,
+ * temporal-CAM max and fg/bg seeding).
+ *
+ * Two groups of entry points:
+ *
+ *  1. DROP-IN (host pointers).  Same names, argument order and meaning as the
+ *     functions the reference exposes to Python through SWIG:
+ *       bilateralfilter / bilateralfilter_batch
+ *           <- dlib/crf/crfwrapper/bilateralfilter/bilateralfilter.hpp:10-12
+ *              (SWIG typemaps bilateralfilter.i:21-25)
+ *       colorbilateralfilter / colorbilateralfilter_batch
+ *           <- dlib/crf/crfwrapper/colorbilateralfilter/colorbilateralfilter.hpp:10-16
+ *     They copy host->device, run the CUDA path on the current device and copy
+ *     the result back (pipelined in chunks of frames).  The reference functions
+ *     return void; these return a status code (0 = ok) as the only extension.
+ *
+ *  2. DEVICE API (device pointers, stream-ordered, capture-safe: no hidden
+ *     synchronisation, no allocation).  This is what the python modules
+ *     DenseCRFLoss / ColorDenseCRFLoss / TCAMSeeder call.  The caller owns
+ *     every buffer, including the workspace.
+ *
+ * Layouts are the reference's: images planar [N,C,H,W] float32 holding 0..255,
+ * segmentations / outputs planar [N,K,H,W] float32.
+ *
+ * Errors never exit(): every function returns a TCAMCRF_* status and
+ * tcamcrf_last_error() describes the last failure of the calling thread.
+ * Conditions that are only detectable on the device (hash table or vertex
+ * pool overflow, lattice coordinate out of the packed-key range) are recorded
+ * in the workspace status word: the outputs of that call are then filled with
+ * NaN -- never silently wrong -- and tcamcrf_workspace_status() reports why.
+ */
+#ifndef TCAMCRF_H_
+#define TCAMCRF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCAMCRF_VERSION 100
+
+/* host-side status codes */
+#define TCAMCRF_OK 0
+#define TCAMCRF_ERR_INVALID 1   /* bad argument (null pointer, non-positive size, unsupported dim) */
+#define TCAMCRF_ERR_WORKSPACE 2 /* workspace too small or misaligned */
+#define TCAMCRF_ERR_CUDA 3      /* a CUDA runtime call or kernel launch failed */
+#define TCAMCRF_ERR_NO_DEVICE 4 /* no sm_100 device visible */
+#define TCAMCRF_ERR_DEVICE_STATUS 5 /* device-side condition, see TCAMCRF_DEV_* */
+
+/* device-side status bits (workspace status word) */
+#define TCAMCRF_DEV_TABLE_FULL 1  /* a frame's hash table overflowed */
+#define TCAMCRF_DEV_POOL_FULL 2   /* vertex pool overflowed */
+#define TCAMCRF_DEV_KEY_RANGE 4   /* lattice coordinate outside the packed-key range */
+
+/* feature kinds */
+#define TCAMCRF_FEAT_XY_RGB 0 /* (x/sxy, y/sxy, c0/srgb, ..): d = 2 + channels; reference bilateralfilter: channels = 3 */
+#define TCAMCRF_FEAT_COLOR 1  /* (c0/srgb, ..): d = channels; reference colorbilateralfilter */
+
+typedef struct tcamcrf_config {
+    int feat;          /* TCAMCRF_FEAT_* */
+    int channels;      /* image planes used as features (DIM of the colour filter) */
+    int image_stride_planes; /* planes between consecutive images in `images`; the reference's
+                                batch functions hard-code 3 (bilateralfilter.cpp:51, colorbilateralfilter.cpp:50) */
+    float sigma_rgb;
+    float sigma_xy;    /* ignored for TCAMCRF_FEAT_COLOR */
+    float hash_load;   /* worst-case load factor the per-frame table is sized for; 0 -> default (0.6) */
+    float pool_factor; /* vertex pool size as a fraction of the worst case (d+1)*H*W per frame; 0 -> 1.0 */
+    int chunk_frames;  /* frames processed per pass (bounds the workspace); 0 -> default (64) */
+} tcamcrf_config;
+
+int tcamcrf_version(void);
+const char *tcamcrf_last_error(void);
+
+/* Number of sm_100 devices the library can run on (0 -> every compute call fails). */
+int tcamcrf_device_count(void);
+
+/* Bytes of device workspace the device API needs for this problem (0 on invalid arguments). */
+size_t tcamcrf_workspace_bytes(const tcamcrf_config *cfg, int N, int K, int H, int W);
+
+/* AS = alpha * Slice(Blur(Splat(segs))) per frame and class.
+ * images_dev [N, stride_planes, H, W], segs_dev/as_dev [N,K,H,W]; all float32 on the current device.
+ * Replaces the compute of bilateralfilter_batch / colorbilateralfilter_batch
+ * (bilateralfilter.cpp:42-55, colorbilateralfilter.cpp:41-54). */
+int tcamcrf_filter(const tcamcrf_config *cfg, const float *images_dev, const float *segs_dev, float *as_dev,
+                   int N, int K, int H, int W, void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Same as tcamcrf_filter, with 8-bit images (planar uint8, same plane layout): the loader-side
+ * format SURVEY.md §8(f).1 asks for.  Features are float(u8)/sigma, i.e. identical values. */
+int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev, float *as_dev,
+                      int N, int K, int H, int W, void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Forward of the DenseCRF loss: as_dev as above and loss_dev[0] = -sum(segs*AS)/n_norm
+ * (dlib/crf/dense_crf_loss.py:56-66).  n_norm is the reference's N (the local batch size). */
+int tcamcrf_loss_forward(const tcamcrf_config *cfg, const float *images_dev, const float *segs_dev, float *as_dev,
+                         float *loss_dev, int N, int K, int H, int W, float n_norm, void *workspace,
+                         size_t workspace_bytes, void *cuda_stream);
+int tcamcrf_loss_forward_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev,
+                            float *as_dev, float *loss_dev, int N, int K, int H, int W, float n_norm,
+                            void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Backward: grad_seg = ((-2 * grad_out[0]) * AS) / n_norm, the reference's expression and rounding
+ * order (dlib/crf/dense_crf_loss.py:73).  count = N*K*H*W. */
+int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
+                          float n_norm, void *cuda_stream);
+
+/* Reads the device status word of a workspace (synchronises the stream).  Returns 0 or TCAMCRF_DEV_* bits
+ * in *dev_status; also writes the number of lattice vertices of the last chunk to *vertices (may be NULL). */
+int tcamcrf_workspace_status(void *workspace, void *cuda_stream, int *dev_status, int *vertices);
+
+/* Lattice introspection for parity tests: builds the lattice of ONE image and copies out, to host memory,
+ * per-(pixel,remainder) vertex ids [H*W*(d+1)] (pixel-major like the reference's offset_), barycentric
+ * weights [H*W*(d+1)], the number of vertices, and the neighbour table [(d+1)*M*2] (when nbr_cap >= that).
+ * Vertex ids are an arbitrary relabelling of the reference's. */
+int tcamcrf_debug_lattice(const tcamcrf_config *cfg, const float *image_host, int H, int W, int32_t *offset_host,
+                          float *bary_host, int *vertices, int32_t *nbr_host, size_t nbr_cap);
+
+/* ---- drop-in host API (reference names and argument lists) ---- */
+int bilateralfilter(float *image, int len_image, float *in, int len_in, float *out, int len_out, int H, int W,
+                    float sigmargb, float sigmaxy);
+int bilateralfilter_batch(float *images, int len_images, float *ins, int len_ins, float *outs, int len_outs, int N,
+                          int K, int H, int W, float sigmargb, float sigmaxy);
+int colorbilateralfilter(float *image, int len_image, float *in, int len_in, float *out, int len_out, int H, int W,
+                         float sigmargb, int DIM);
+int colorbilateralfilter_batch(float *images, int len_images, float *ins, int len_ins, float *outs, int len_outs,
+                               int N, int K, int H, int W, float sigmargb, int DIM);
+
+/* Host-pointer fwd+bwd of the loss in one call (what bench.py's e2e leg times):
+ * images/segs in host memory, writes loss_host[0], grad_host [N,K,H,W] (for grad_out = 1 * weight). */
+int tcamcrf_loss_fwd_bwd_host(const tcamcrf_config *cfg, const float *images_host, const float *segs_host,
+                              float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out);
+
+/* ---- measurement hooks (bench.py) ----
+ * Stage timing brackets every pipeline stage with CUDA events on the caller's stream (not capture-safe while
+ * enabled).  Stages: 0 build, 1 neighbour, 2 splat, 3 blur (d+1 launches), 4 slice, 5 loss reduce/finish, 6 backward. */
+#define TCAMCRF_STAGES 7
+void tcamcrf_profile_enable(int on);
+/* Waits for the recorded events; fills accumulated milliseconds and kernel launches per stage. */
+int tcamcrf_profile_read(double *ms, long long *launches, int reset);
+/* Kernels launched by this library since it was loaded (all threads). */
+long long tcamcrf_launch_count(void);
+
+/* ---- temporal CAM max + seeding (dlib/datasets/wsol_loader.py:585-600, dlib/cams/tcam_seeding.py:178-260) ---- */
+
+/* out[b] = max_t cams[b,t] with torch.maximum's NaN propagation; cams_dev [B,T,HW], out_dev [B,HW]. */
+int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCAMCRF_H_ */

@@ -1,0 +1,246 @@
+// lattice.cuh -- device-side building blocks of the permutohedral lattice:
+// packed 64-bit vertex keys, the per-pixel embedding, and the open-addressing
+// key table.  sm_100a only.
+//
+// What it replaces in the reference (dlib/crf/crfwrapper/bilateralfilter/):
+//   embed_point<D>   <- the per-pixel body of Permutohedral::init, SSE path
+//                       (permutohedral.cpp:168-252)
+//   KeyCodec<D>      <- the `short key[d]` arrays + canonical simplex table
+//                       (permutohedral.cpp:144-153,245-248)
+//   table_insert /   <- HashTable::find(k, create=true/false)
+//   table_lookup        (permutohedral.cpp:67-95)
+//
+// Design notes (B200-first, not a translation):
+//   * A lattice vertex has d coordinates that are all congruent to the same
+//     remainder r (mod d+1).  Instead of d int16 values the key stores the d
+//     quotients q_i = floor(k_i/(d+1)) in B-bit biased fields plus r in 3 bits,
+//     which fits one 64-bit word for every d <= 6.  One 64-bit atomicCAS then
+//     inserts a vertex, and the +-1 / -+d neighbour steps of the blur become
+//     integer adds on the packed word (neighbour_keys()).
+//   * fp32 operations whose rounding decides which simplex a pixel falls in are
+//     written with explicit round-to-nearest intrinsics so nvcc cannot contract
+//     them into FMAs: the reference's SSE2 code rounds after every multiply.
+#pragma once
+#include <cstdint>
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+// Host emulation, used only by tests/host_harness.cpp to run the very same
+// embedding and key arithmetic on the CPU (compile with -ffp-contract=off).
+#include <cmath>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+#endif
+
+namespace tcamcrf {
+
+constexpr int kMaxD = 6;
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+template <int D>
+struct KeyCodec {
+    static_assert(D >= 1 && D <= kMaxD, "lattice dimension out of range");
+    static constexpr int kRemBits = 3;
+    static constexpr int kFieldBits = ((64 - kRemBits) / D) < 20 ? ((64 - kRemBits) / D) : 20;
+    static constexpr int kBias = 1 << (kFieldBits - 1);
+    static constexpr unsigned long long kFieldMask = (1ull << kFieldBits) - 1ull;
+    // smallest / largest quotient that can still take a +-1 neighbour step
+    static constexpr int kQMin = -kBias + 1;
+    static constexpr int kQMax = kBias - 2;
+
+    // 1 in every quotient field
+    __host__ __device__ static constexpr unsigned long long ones()
+    {
+        unsigned long long v = 0;
+        for (int i = 0; i < D; i++) v |= 1ull << (kRemBits + i * kFieldBits);
+        return v;
+    }
+    __host__ __device__ static constexpr unsigned long long unit(int i)
+    {
+        return 1ull << (kRemBits + i * kFieldBits);
+    }
+    __device__ static unsigned long long pack(const int (&q)[D], int rem)
+    {
+        unsigned long long k = (unsigned long long)rem;
+#pragma unroll
+        for (int i = 0; i < D; i++)
+            k |= ((unsigned long long)(unsigned)(q[i] + kBias) & kFieldMask) << (kRemBits + i * kFieldBits);
+        return k;
+    }
+    // lattice coordinate i of a packed key (for debugging / tests)
+    __host__ __device__ static int coord(unsigned long long key, int i)
+    {
+        int rem = (int)(key & 7ull);
+        int q = (int)((key >> (kRemBits + i * kFieldBits)) & kFieldMask) - kBias;
+        return q * (D + 1) + rem;
+    }
+
+    // Keys of the two blur neighbours along axis j (0..D) of vertex `key`:
+    //   n1 = key - 1 on every coordinate, + (D+1) on coordinate j
+    //   n2 = key + 1 on every coordinate, - (D+1) on coordinate j
+    // (permutohedral.cpp:285-290; axis D is the implicit coordinate, so only the
+    // all-coordinates step remains).  In (q, rem) form a -1 step lowers rem, and
+    // wraps every quotient down when rem was 0; the +(D+1) on axis j is q_j + 1.
+    __device__ static void neighbour_keys(unsigned long long key, int j, unsigned long long &n1,
+                                          unsigned long long &n2)
+    {
+        const int rem = (int)(key & 7ull);
+        const unsigned long long uj = (j < D) ? unit(j) : 0ull;
+        if (rem > 0)
+            n1 = key - 1ull + uj;              // rem-1, q_j+1
+        else
+            n1 = key + (unsigned long long)D - ones() + uj;  // rem=D, all q-1, then q_j back up
+        if (rem < D)
+            n2 = key + 1ull - uj;              // rem+1, q_j-1
+        else
+            n2 = key - (unsigned long long)D + ones() - uj;  // rem=0, all q+1, then q_j back down
+    }
+};
+
+// murmur3 finaliser: the table index is the low bits of this
+__device__ __forceinline__ unsigned int hash_key(unsigned long long k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned int)k;
+}
+
+struct EmbedConsts {
+    float scale[kMaxD];  // diagonal of E, double-evaluated on the host (permutohedral.cpp:156-159)
+};
+
+// Embeds one feature vector.  Outputs: z[i] (rem0[i] = z[i]*(D+1)), rank[i], bary[r].
+// Returns false when a quotient leaves the packed-key range.
+template <int D>
+__device__ __forceinline__ bool embed_point(const float (&f)[D], const EmbedConsts &ec, int (&z)[D + 1],
+                                            int (&rank)[D + 1], float (&bary)[D + 1])
+{
+    constexpr float inv_dp1 = 1.0f / (D + 1);
+    constexpr float dp1 = (float)(D + 1);
+    float el[D + 1];
+
+    // y = E p (permutohedral.cpp:177-184)
+    float sm = 0.0f;
+#pragma unroll
+    for (int j = D; j > 0; j--) {
+        const float cf = __fmul_rn(f[j - 1], ec.scale[j - 1]);
+        el[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
+        sm = __fadd_rn(sm, cf);
+    }
+    el[0] = sm;
+
+    // nearest 0-coloured vertex; cvtps2dq rounds half to even (:187-197)
+    int sum = 0;
+    float rem0[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        const int vi = __float2int_rn(__fmul_rn(inv_dp1, el[i]));
+        z[i] = vi;
+        rem0[i] = __fmul_rn((float)vi, dp1);
+        sum += vi;
+    }
+
+    // rank of the residuals, fp32 compares (:200-210)
+    float res[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        res[i] = __fsub_rn(el[i], rem0[i]);
+        rank[i] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = i + 1; j <= D; j++) {
+            const int c = res[i] < res[j] ? 1 : 0;
+            rank[i] += c;
+            rank[j] += 1 - c;
+        }
+
+    // back onto the plane sum == 0 (:213-219)
+    bool in_range = true;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        rank[i] += sum;
+        if (rank[i] < 0) {
+            rank[i] += D + 1;
+            z[i] += 1;
+        } else if (rank[i] > D) {
+            rank[i] -= D + 1;
+            z[i] -= 1;
+        }
+        // q = z or z-1 must stay inside the field, with room for a neighbour step
+        in_range = in_range && (z[i] - 1 >= KeyCodec<D>::kQMin) && (z[i] <= KeyCodec<D>::kQMax);
+        // a rank outside 0..D can only come from a non-finite feature
+        in_range = in_range && (rank[i] >= 0) && (rank[i] <= D);
+    }
+
+    // barycentric weights (:222-240): with v sorted by rank,
+    //   b[t] = v[rank = D-t] - v[rank = D-t+1],  b[0] += 1 + b[D+1]
+    float vs[D + 2];
+#pragma unroll
+    for (int t = 0; t <= D + 1; t++) vs[t] = 0.0f;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        const float v = __fmul_rn(__fsub_rn(el[i], __fmul_rn((float)z[i], dp1)), inv_dp1);
+#pragma unroll
+        for (int t = 0; t <= D; t++)
+            if (rank[i] == t) vs[t] = v;
+    }
+#pragma unroll
+    for (int t = 1; t <= D; t++) bary[t] = __fsub_rn(vs[D - t], vs[D - t + 1]);
+    // b[D+1] = -v[rank 0];  b[0] = v[rank D] + (1 + b[D+1])
+    bary[0] = __fadd_rn(vs[D], __fadd_rn(1.0f, -vs[0]));
+    return in_range;
+}
+
+#if defined(__CUDACC__)
+// Inserts `key` into the open-addressing table keys[0..mask] (linear probing).
+// Returns the slot, or -1 when the table is full.  `won` tells whether this call
+// created the entry.  Loads bypass L1 (ld.global.cg): the table is written
+// concurrently by other SMs, and a stale EMPTY would only cost one extra CAS.
+__device__ __forceinline__ int table_insert(unsigned long long *keys, unsigned int mask, unsigned long long key,
+                                            bool &won)
+{
+    unsigned int h = hash_key(key) & mask;
+    won = false;
+    for (unsigned int probes = 0; probes <= mask; probes++) {
+        unsigned long long cur = __ldcg(keys + h);
+        if (cur == key) return (int)h;
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(keys + h, kEmptyKey, key);
+            if (cur == kEmptyKey) {
+                won = true;
+                return (int)h;
+            }
+            if (cur == key) return (int)h;
+        }
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// Finds `key`; returns the slot or -1.
+__device__ __forceinline__ int table_lookup(const unsigned long long *__restrict__ keys, unsigned int mask,
+                                            unsigned long long key)
+{
+    unsigned int h = hash_key(key) & mask;
+    for (unsigned int probes = 0; probes <= mask; probes++) {
+        const unsigned long long cur = __ldg(keys + h);
+        if (cur == key) return (int)h;
+        if (cur == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+#endif  // __CUDACC__
+
+}  // namespace tcamcrf

@@ -1,0 +1,86 @@
+"""DenseCRFLoss -- drop-in for ``dlib/crf/dense_crf_loss.py`` of the reference.
+
+Same constructor, same ``forward(images, segmentations)`` keywords, same ``extra_repr``,
+same value and gradient (``loss = -sum(S*AS)/N``, ``dS = -2*g*AS/N``,
+dense_crf_loss.py:63-74), but the bilateral filter runs on the GPU through
+``libtcamcrf.so`` instead of the SWIG/OpenMP C++ module, with no device synchronisation
+and no device->host->device round trip of the segmentations.
+
+``images`` may be what the reference's trainer passes (a CPU float32 tensor holding 0..255,
+train_wsol.py:1128) or, to skip the host copy, a CUDA float32 / uint8 tensor.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib, ops
+
+__all__ = ['DenseCRFLoss', 'DenseCRFLossFunction']
+
+
+def _scale_images(images: torch.Tensor, scale_factor: float) -> torch.Tensor:
+    if scale_factor == 1.0:
+        return images  # nearest-neighbour resampling at scale 1 is the identity
+    x = images if images.is_floating_point() else images.float()
+    return F.interpolate(x, scale_factor=scale_factor, mode='nearest', recompute_scale_factor=False)
+
+
+def _scale_segs(segmentations: torch.Tensor, scale_factor: float) -> torch.Tensor:
+    if scale_factor == 1.0:
+        return segmentations
+    return F.interpolate(segmentations, scale_factor=scale_factor, mode='bilinear',
+                         recompute_scale_factor=False, align_corners=False)
+
+
+class DenseCRFLossFunction(Function):
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda')
+    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy):
+        n = segmentations.shape[0]
+        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
+        as_t, loss, _ = ops.crf_forward(images, segmentations.detach(), cfg, want_loss=True, n_norm=float(n))
+        ctx.AS = as_t
+        ctx.N = n
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, grad_output):
+        grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N))
+        return None, grad_segmentation, None, None
+
+
+class DenseCRFLoss(nn.Module):
+    def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor):
+        """
+        :param weight: float. lambda of the CRF loss.
+        :param sigma_rgb: float. colour bandwidth of the bilateral kernel.
+        :param sigma_xy: float. spatial bandwidth of the bilateral kernel.
+        :param scale_factor: float. images and segmentations are rescaled by it first.
+        """
+        super(DenseCRFLoss, self).__init__()
+        self.weight = weight
+        self.sigma_rgb = sigma_rgb
+        self.sigma_xy = sigma_xy
+        self.scale_factor = scale_factor
+
+    def forward(self, images, segmentations):
+        """
+        :param images: N*3*H*W tensor with values in [0, 255]; CPU float32 (as in the reference) or CUDA float32/uint8.
+        :param segmentations: softmaxed logits, N*K*H*W, CUDA.
+        :return: loss tensor of shape [1] on segmentations.device.
+        """
+        scaled_images = _scale_images(images, self.scale_factor)
+        scaled_segs = _scale_segs(segmentations, self.scale_factor)
+        val = self.weight * DenseCRFLossFunction.apply(
+            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor)
+        return val
+
+    def extra_repr(self):
+        return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}'.format(
+            self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor
+        )

@@ -1,0 +1,153 @@
+"""torch-facing wrappers over the device API of libtcamcrf.so.
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, workspace) and the
+stream; all compute happens in the hand-written CUDA kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import byref, c_int
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FEAT_COLOR, FEAT_XY_RGB, TcamCrfError
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+STRICT = os.environ.get("TCAMCRF_STRICT", "0") == "1"
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise TcamCrfError(f"{name} must be a CUDA tensor: this package has no CPU path")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        # grow geometrically; the old buffer is released to torch's caching allocator (stream-safe)
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def _prep_images(images: torch.Tensor, device: torch.device) -> Tuple[torch.Tensor, bool]:
+    """Bring the image batch onto `device` as contiguous float32 or uint8 [N,C,H,W]."""
+    if images.dtype == torch.uint8:
+        u8 = True
+    else:
+        u8 = False
+        if images.dtype != torch.float32:
+            images = images.float()
+    if images.device != device:
+        images = images.to(device, non_blocking=True)
+    return images.contiguous(), u8
+
+
+def workspace_status(ws: torch.Tensor) -> Tuple[int, int]:
+    """(device status bits, vertex count of the last chunk); synchronises the stream."""
+    lib = _lib.load()
+    st, m = c_int(0), c_int(0)
+    _lib.check(lib.tcamcrf_workspace_status(ws.data_ptr(), _stream_ptr(ws.device), byref(st), byref(m)),
+               "tcamcrf_workspace_status")
+    return st.value, m.value
+
+
+def _raise_on_status(ws: torch.Tensor) -> None:
+    st, _ = workspace_status(ws)
+    if st:
+        why = [n for b, n in ((1, "hash table full"), (2, "vertex pool full"), (4, "lattice coordinate out of key range")) if st & b]
+        raise TcamCrfError("device status 0x%x: %s" % (st, ", ".join(why)))
+
+
+def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want_loss: bool = True,
+                n_norm: Optional[float] = None, check: Optional[bool] = None):
+    """Runs build+splat+blur+slice (and the loss reduction) on the current stream.
+
+    images [N,C,H,W] float32 0..255 or uint8 (any device; moved to segs.device), segs [N,K,H,W] float32 CUDA.
+    Returns (AS [N,K,H,W], loss [1] or None, workspace tensor).
+    """
+    lib = _lib.load()
+    _require_cuda(segs, "segmentations")
+    device = segs.device
+    if segs.dtype != torch.float32:
+        segs = segs.float()
+    segs = segs.contiguous()
+    n, k, h, w = segs.shape
+    images, u8 = _prep_images(images, device)
+    if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
+        raise TcamCrfError(f"images {tuple(images.shape)} do not match segmentations {tuple(segs.shape)}")
+    if images.shape[1] < cfg.channels:
+        raise TcamCrfError(f"images have {images.shape[1]} planes, config needs {cfg.channels}")
+    cfg.image_stride_planes = images.shape[1]
+    with torch.cuda.device(device):
+        nbytes = lib.tcamcrf_workspace_bytes(byref(cfg), n, k, h, w)
+        if nbytes == 0:
+            raise TcamCrfError("tcamcrf_workspace_bytes: " + _lib.last_error())
+        ws = _workspace(device, nbytes)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
+        as_out = torch.empty_like(segs)
+        stream = _stream_ptr(device)
+        if want_loss:
+            loss = torch.empty(1, dtype=torch.float32, device=device)
+            fn = lib.tcamcrf_loss_forward_u8 if u8 else lib.tcamcrf_loss_forward
+            rc = fn(byref(cfg), images.data_ptr(), segs.data_ptr(), as_out.data_ptr(), loss.data_ptr(), n, k, h, w,
+                    float(n if n_norm is None else n_norm), ws_ptr, ws_bytes, stream)
+        else:
+            loss = None
+            fn = lib.tcamcrf_filter_u8 if u8 else lib.tcamcrf_filter
+            rc = fn(byref(cfg), images.data_ptr(), segs.data_ptr(), as_out.data_ptr(), n, k, h, w, ws_ptr, ws_bytes,
+                    stream)
+        _lib.check(rc, "tcamcrf forward")
+        if STRICT if check is None else check:
+            _raise_on_status(ws if ws_ptr == ws.data_ptr() else ws[ws_ptr - ws.data_ptr():])
+    return as_out, loss, ws
+
+
+def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float) -> torch.Tensor:
+    """grad_seg = ((-2*g) * AS) / n_norm on the current stream (dlib/crf/dense_crf_loss.py:73)."""
+    lib = _lib.load()
+    _require_cuda(as_t, "AS")
+    g = grad_output.detach().reshape(-1)[:1].to(device=as_t.device, dtype=torch.float32).contiguous()
+    grad = torch.empty_like(as_t)
+    with torch.cuda.device(as_t.device):
+        _lib.check(lib.tcamcrf_loss_backward(as_t.data_ptr(), g.data_ptr(), grad.data_ptr(), as_t.numel(),
+                                             float(n_norm), _stream_ptr(as_t.device)), "tcamcrf_loss_backward")
+    return grad
+
+
+def temporal_cam_max(cams: torch.Tensor) -> torch.Tensor:
+    """max over dim 1 of a CUDA float32 stack [B,T,...] -> [B,...] with torch.maximum's NaN propagation.
+
+    Mirrors the chain of ``torch.maximum`` calls in dlib/datasets/wsol_loader.py:591-600."""
+    lib = _lib.load()
+    _require_cuda(cams, "cams")
+    if cams.dtype != torch.float32:
+        raise TcamCrfError("cams must be float32")
+    cams = cams.contiguous()
+    b, t = cams.shape[0], cams.shape[1]
+    rest = cams.shape[2:]
+    hw = 1
+    for s in rest:
+        hw *= s
+    out = torch.empty((b,) + tuple(rest), dtype=torch.float32, device=cams.device)
+    with torch.cuda.device(cams.device):
+        _lib.check(lib.tcam_temporal_max(cams.data_ptr(), out.data_ptr(), b, t, hw, _stream_ptr(cams.device)),
+                   "tcam_temporal_max")
+    return out
+
+
+__all__ = ["crf_forward", "crf_backward", "temporal_cam_max", "workspace_status", "release_workspaces",
+           "FEAT_COLOR", "FEAT_XY_RGB"]

@@ -1,0 +1,350 @@
+"""GPU suite (-m gpu): parity of the CUDA path against the oracle, through the C ABI.
+
+Tolerances (BASELINE.json north_star): filtered tensors, loss and gradient within rel 1e-4 in
+fp32; lattice structure (which vertices each pixel touches, barycentric weights) bit-exact.
+The only non-bit-exact step is the splat's atomic summation order, so the errors seen are ~1e-6.
+
+Nothing here reads /root/reference: the checker is the C restatement (oracle/permuto_oracle.c)
+and the committed golden fixtures (made from the reference build by tests/golden/make_golden.py).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_golden, pointwise_rel_err, rel_err
+from tcam_wsol_video_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # north_star: "within rel 1e-4 on filtered tensors, CRF loss value and CRF gradient in fp32"
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU suite needs a B200"
+    assert _lib.load().tcamcrf_device_count() >= 1
+    return torch
+
+
+def _gpu_filter_host(img, seg, srgb, sxy, dim=0):
+    """AS through the drop-in host API (reference names, numpy 1-D contract)."""
+    from tcam_wsol_video_b200 import bilateralfilter as bf
+    from tcam_wsol_video_b200 import colorbilateralfilter as cbf
+    n, k, h, w = seg.shape
+    out = np.zeros(seg.size, np.float32)
+    if dim:
+        cbf.colorbilateralfilter_batch(np.ascontiguousarray(img.ravel()), np.ascontiguousarray(seg.ravel()), out,
+                                       n, k, h, w, srgb, dim)
+    else:
+        bf.bilateralfilter_batch(np.ascontiguousarray(img.ravel()), np.ascontiguousarray(seg.ravel()), out,
+                                 n, k, h, w, srgb, sxy)
+    return out.reshape(seg.shape)
+
+
+def _assert_close(got, want, what):
+    e = rel_err(got, want)
+    assert e < REL_TOL, f"{what}: normwise rel err {e:.3e}"
+    # pointwise, with a floor at 1e-3 of the largest magnitude (outputs are positive and of similar scale)
+    pe = pointwise_rel_err(got, want, floor=1e-3 * float(np.abs(want).max()))
+    assert pe < REL_TOL, f"{what}: pointwise rel err {pe:.3e}"
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures (reference-made)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_cases(), ids=os.path.basename)
+def test_host_api_matches_golden(torch_cuda, path):
+    g = load_golden(path)
+    img = g["image_u8"].astype(np.float32)
+    got = _gpu_filter_host(img, g["seg"], float(g["sigma_rgb"]), float(g["sigma_xy"]), int(g["dim"]))
+    _assert_close(got, g["AS"], "AS")
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=os.path.basename)
+def test_module_loss_and_grad_match_golden(torch_cuda, path):
+    torch = torch_cuda
+    from tcam_wsol_video_b200.color_dense_crf_loss import ColorDenseCRFLoss
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    g = load_golden(path)
+    images = torch.from_numpy(g["image_u8"].astype(np.float32))          # CPU, like the trainer passes it
+    seg = torch.from_numpy(g["seg"]).cuda().requires_grad_(True)
+    weight = 1.0
+    if int(g["dim"]):
+        mod = ColorDenseCRFLoss(weight=weight, sigma_rgb=float(g["sigma_rgb"]), scale_factor=1.0)
+    else:
+        mod = DenseCRFLoss(weight=weight, sigma_rgb=float(g["sigma_rgb"]), sigma_xy=float(g["sigma_xy"]),
+                           scale_factor=1.0)
+    loss = mod(images=images, segmentations=seg)
+    assert loss.shape == (1,) and loss.device == seg.device and loss.dtype == torch.float32
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < REL_TOL * abs(float(g["loss"]))
+    _assert_close(seg.grad.cpu().numpy(), g["grad"], "grad")
+
+
+def test_golden_224_noise(torch_cuda):
+    g = load_golden(os.path.join(GOLDEN, "bf5_noise_n1_k2_224x224.npz"))
+    n, k, h, w = (int(v) for v in g["shape"])
+    img = synth.make_images(n, h, w, str(g["kind"]), seed=int(g["seed"]))
+    seg = synth.make_segs(n, k, h, w, seed=int(g["seed"]))
+    got = _gpu_filter_host(img, seg, float(g["sigma_rgb"]), float(g["sigma_xy"]))
+    _assert_close(got.ravel()[:: int(g["stride"])], g["AS_sample"], "AS sample")
+    assert abs(got.astype(np.float64).sum() - float(g["AS_sum"])) < 1e-5 * float(g["AS_sum"])
+    loss = -float((seg.astype(np.float64) * got).sum()) / n
+    assert abs(loss - float(g["loss"])) < REL_TOL * abs(float(g["loss"]))
+
+
+# ---------------------------------------------------------------------------
+# lattice structure: bit-exact
+# ---------------------------------------------------------------------------
+def _debug_lattice(cfg, img, h, w):
+    lib = _lib.load()
+    d = (2 + cfg.channels) if cfg.feat == _lib.FEAT_XY_RGB else cfg.channels
+    p = h * w
+    off = np.zeros(p * (d + 1), np.int32)
+    bary = np.zeros(p * (d + 1), np.float32)
+    m = ctypes.c_int(0)
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    nbr = np.zeros((d + 1) * p * (d + 1) * 2, np.int32)
+    _lib.check(lib.tcamcrf_debug_lattice(ctypes.byref(cfg), img.ctypes.data, h, w, off.ctypes.data, bary.ctypes.data,
+                                         ctypes.byref(m), nbr.ctypes.data, nbr.size), "tcamcrf_debug_lattice")
+    M = m.value
+    return off.reshape(p, d + 1), bary.reshape(p, d + 1), M, nbr[: (d + 1) * M * 2].reshape(d + 1, M, 2)
+
+
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+@pytest.mark.parametrize("dim", [0, 3, 1])
+@pytest.mark.parametrize("hw", [(32, 40), (31, 37), (224, 224)])
+def test_lattice_structure_bit_exact(torch_cuda, oracle_mod, kind, dim, hw):
+    h, w = hw
+    img = synth.make_images(1, h, w, kind, seed=21)[0]
+    if dim:
+        cfg = _lib.make_config(_lib.FEAT_COLOR, dim, 15.0)
+        L = oracle_mod.port_lattice_color(img, h, w, 15.0, dim)
+        img_in = img[:dim]
+    else:
+        cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+        L = oracle_mod.port_lattice_bilateral(img, h, w, 15.0, 100.0)
+        img_in = img
+    off, bary, M, nbr = _debug_lattice(cfg, img_in, h, w)
+    p = h * w
+    d = L.d
+    # the oracle also inserts the reference's zero-feature padding pixels when P % 4 != 0; those vertices
+    # are never splatted to, so compare on the vertices real pixels touch
+    used = np.unique(L.offset[:p])
+    assert M == len(used)
+    assert np.array_equal(bary, L.bary[:p])                     # bit-exact weights
+    # ids are a relabelling: the map oracle id -> gpu id must be a bijection
+    fwd = np.full(L.m, -1, np.int64)
+    fwd[L.offset[:p].ravel()] = off.ravel()
+    assert np.array_equal(fwd[L.offset[:p].ravel()], off.ravel())   # consistent
+    assert len(np.unique(fwd[used])) == len(used)                   # injective
+    # neighbour tables agree under the relabelling (missing stays missing; a neighbour that is only a
+    # padding vertex of the oracle has no gpu id and no value, i.e. it is "missing" on both sides)
+    ext = np.concatenate([fwd, [-1]])
+    for j in range(d + 1):
+        want = ext[L.nbr[j][used]]                                  # [len(used), 2] in gpu ids
+        got = nbr[j][fwd[used]]
+        assert np.array_equal(want, got), f"axis {j}"
+
+
+# ---------------------------------------------------------------------------
+# oracle comparisons on seeded inputs
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+@pytest.mark.parametrize("shape", [(1, 2, 224, 224), (3, 10, 64, 48), (2, 1, 33, 35), (2, 3, 17, 129), (1, 4, 1, 1),
+                                   (2, 2, 1, 50), (1, 5, 3, 2)])
+def test_filter_vs_oracle(torch_cuda, oracle_mod, kind, shape):
+    n, k, h, w = shape
+    img = synth.make_images(n, h, w, kind, seed=31)
+    seg = synth.make_segs(n, k, h, w, seed=31)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 100.0)
+    _assert_close(got, want, "5-D AS")
+    want = oracle_mod.port_colorbilateralfilter_batch(img, seg, n, k, h, w, 15.0, 3).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=3)
+    _assert_close(got, want, "3-D colour AS")
+
+
+@pytest.mark.parametrize("sig", [(1.0, 1.0), (3.0, 10.0), (80.0, 300.0), (255.0, 1000.0)])
+def test_sigma_extremes(torch_cuda, oracle_mod, sig):
+    srgb, sxy = sig
+    n, k, h, w = 1, 2, 40, 40
+    img = synth.make_images(n, h, w, "noise", seed=41)
+    seg = synth.make_segs(n, k, h, w, seed=41)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, srgb, sxy).reshape(seg.shape)
+    _assert_close(_gpu_filter_host(img, seg, srgb, sxy), want, f"sigma {sig}")
+
+
+def test_constant_image_and_signed_input(torch_cuda, oracle_mod):
+    """One colour everywhere (heavy key duplication: every warp inserts the same vertices) and a
+    segmentation with negative entries (the filter is linear, not restricted to probabilities)."""
+    n, k, h, w = 2, 2, 48, 64
+    img = np.full((n, 3, h, w), 128.0, np.float32)
+    rng = np.random.default_rng(5)
+    seg = rng.standard_normal((n, k, h, w)).astype(np.float32)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 100.0)
+    assert rel_err(got, want) < REL_TOL
+    want = oracle_mod.port_colorbilateralfilter_batch(img, seg, n, k, h, w, 15.0, 3).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=3)
+    assert rel_err(got, want) < REL_TOL
+
+
+def test_single_image_entry_points(torch_cuda, oracle_mod):
+    from tcam_wsol_video_b200 import bilateralfilter as bf
+    from tcam_wsol_video_b200 import colorbilateralfilter as cbf
+    k, h, w = 3, 30, 26
+    img = synth.make_images(1, h, w, "natural", seed=51)
+    seg = synth.make_segs(1, k, h, w, seed=51)
+    out = np.zeros(seg.size, np.float32)
+    bf.bilateralfilter(img.ravel(), seg.ravel(), out, h, w, 15.0, 100.0)     # K inferred from len(in)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, 1, k, h, w, 15.0, 100.0)
+    _assert_close(out, want, "bilateralfilter")
+    out = np.zeros(seg.size, np.float32)
+    cbf.colorbilateralfilter(img.ravel(), seg.ravel(), out, h, w, 15.0, 3)
+    want = oracle_mod.port_colorbilateralfilter_batch(img, seg, 1, k, h, w, 15.0, 3)
+    _assert_close(out, want, "colorbilateralfilter")
+    # empty batch: the reference's loop runs zero times and leaves `outs` untouched
+    out = np.full(4, 7.0, np.float32)
+    bf.bilateralfilter_batch(np.zeros(0, np.float32), np.zeros(0, np.float32), out, 0, 2, 4, 4, 15.0, 100.0)
+    assert np.all(out == 7.0)
+
+
+def test_u8_images_and_chunking_give_identical_results(torch_cuda):
+    """uint8 images produce the same features as float images holding the same integers, and processing the
+    batch in chunks of frames does not change anything but the summation order inside the loss."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 5, 2, 40, 56
+    img = synth.make_images(n, h, w, "natural", seed=61)
+    seg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=61)).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    as_f, loss_f, _ = ops.crf_forward(torch.from_numpy(img).cuda(), seg, cfg, check=True)
+    as_u, loss_u, _ = ops.crf_forward(torch.from_numpy(img.astype(np.uint8)).cuda(), seg, cfg, check=True)
+    cfg2 = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, chunk_frames=2)
+    as_c, loss_c, _ = ops.crf_forward(torch.from_numpy(img), seg, cfg2, check=True)
+    assert rel_err(as_u.cpu().numpy(), as_f.cpu().numpy()) < 1e-5
+    assert rel_err(as_c.cpu().numpy(), as_f.cpu().numpy()) < 1e-5
+    assert abs(loss_u.item() - loss_f.item()) < 1e-5 * abs(loss_f.item())
+    assert abs(loss_c.item() - loss_f.item()) < 1e-5 * abs(loss_f.item())
+
+
+def test_backward_is_bit_exact_given_AS(torch_cuda):
+    """grad = ((-2*g)*AS)/N with the reference's rounding order: identical bits to the torch expression."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    torch.manual_seed(0)
+    as_t = torch.rand(3, 2, 31, 17, device="cuda") * 50
+    g = torch.tensor([1e-7 * 3.3], device="cuda")
+    got = ops.crf_backward(as_t, g, 3.0)
+    want = -2 * g * as_t / torch.tensor([3.0], device="cuda")
+    assert torch.equal(got, want)
+
+
+def test_module_scale_factor_and_amp(torch_cuda, oracle_mod):
+    """scale_factor != 1 (nearest / bilinear rescale first, sigma_xy scaled; dense_crf_loss.py:105-121) and
+    a call under autocast (custom_fwd keeps the op in fp32)."""
+    torch = torch_cuda
+    import torch.nn.functional as F
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    n, k, h, w = 2, 2, 48, 64
+    img = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=71))
+    seg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=71)).cuda().requires_grad_(True)
+    mod = DenseCRFLoss(weight=1e-3, sigma_rgb=15.0, sigma_xy=100.0, scale_factor=0.5).cuda()
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss = mod(images=img, segmentations=seg)
+    loss.backward()
+    # oracle on the rescaled inputs
+    simg = F.interpolate(img, scale_factor=0.5, mode="nearest", recompute_scale_factor=False).numpy()
+    sseg = F.interpolate(seg.detach().cpu(), scale_factor=0.5, mode="bilinear", recompute_scale_factor=False,
+                         align_corners=False)
+    want_loss, want_grad, _ = oracle_mod.densecrf_loss_fwd_bwd(simg, sseg.numpy(), 15.0, 50.0, 1.0,
+                                                               oracle_mod.port_bilateralfilter_batch)
+    assert abs(loss.item() - 1e-3 * float(want_loss)) < REL_TOL * abs(1e-3 * float(want_loss))
+    # gradient w.r.t. the full-resolution segmentation = bilinear-adjoint of the oracle's gradient
+    sseg_t = F.interpolate(seg.detach().cpu().requires_grad_(True), scale_factor=0.5, mode="bilinear",
+                           recompute_scale_factor=False, align_corners=False)
+    ref_in = seg.detach().cpu().requires_grad_(True)
+    F.interpolate(ref_in, scale_factor=0.5, mode="bilinear", recompute_scale_factor=False,
+                  align_corners=False).backward(torch.from_numpy(want_grad) * 1e-3)
+    assert rel_err(seg.grad.cpu().numpy(), ref_in.grad.numpy()) < REL_TOL
+
+
+def test_device_status_poisons_outputs(torch_cuda):
+    """A vertex pool that is too small must yield NaN outputs and a readable status, never wrong numbers."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 1, 2, 64, 64
+    img = torch.from_numpy(synth.make_images(n, h, w, "noise", seed=81))
+    seg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=81)).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, pool_factor=0.01)
+    as_t, loss, ws = ops.crf_forward(img, seg, cfg, check=False)
+    st, _ = ops.workspace_status(ws)
+    assert st & _lib.DEV_POOL_FULL
+    assert torch.isnan(loss).all() and torch.isnan(as_t).all()
+    with pytest.raises(_lib.TcamCrfError):
+        ops.crf_forward(img, seg, cfg, check=True)
+    # key range: sigma so small that lattice coordinates leave the packed fields
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 1e-3, 100.0)
+    as_t, loss, ws = ops.crf_forward(img, seg, cfg, check=False)
+    st, _ = ops.workspace_status(ws)
+    assert st & _lib.DEV_KEY_RANGE and torch.isnan(loss).all()
+
+
+@pytest.mark.parametrize("load", [0.25, 0.5, 0.9])
+def test_hash_load_factor_sweep(torch_cuda, oracle_mod, load):
+    """BASELINE config 4 (occupancy sweep): results do not depend on the table size."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 1, 2, 96, 96
+    img = synth.make_images(n, h, w, "noise", seed=91)
+    seg = synth.make_segs(n, k, h, w, seed=91)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0).reshape(seg.shape)
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, hash_load=load)
+    as_t, _, _ = ops.crf_forward(torch.from_numpy(img), torch.from_numpy(seg).cuda(), cfg, check=True)
+    _assert_close(as_t.cpu().numpy(), want, f"load {load}")
+
+
+def test_full_size_properties_config2(torch_cuda):
+    """BASELINE configs[1] at full size (32 x 10 classes x 224^2): too slow for the scalar oracle in a unit
+    test, so check size-independent properties: linearity, channel independence (K=10 in one pass equals
+    ten K=1 passes), determinism of the lattice, and frame independence."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 32, 10, 224, 224
+    img = torch.from_numpy(synth.make_images(n, h, w, "noise", seed=0)).cuda()
+    seg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=0)).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    as1, loss1, _ = ops.crf_forward(img, seg, cfg, check=True)
+    assert torch.isfinite(as1).all() and as1.min() > 0
+    # loss definition
+    want = -(seg.double() * as1.double()).sum() / n
+    assert abs(loss1.item() - want.item()) < 1e-5 * abs(want.item())
+    # linearity
+    as2, _, _ = ops.crf_forward(img, (seg * 3.0).contiguous(), cfg, check=True)
+    assert rel_err(as2.cpu().numpy(), (as1 * 3.0).cpu().numpy()) < 1e-5
+    # channel independence: class 7 alone
+    as7, _, _ = ops.crf_forward(img, seg[:, 7:8].contiguous(), cfg, check=True)
+    assert rel_err(as7.cpu().numpy(), as1[:, 7:8].cpu().numpy()) < 1e-5
+    # frame independence: frames 5..8 alone
+    as_sub, _, _ = ops.crf_forward(img[5:9].contiguous(), seg[5:9].contiguous(), cfg, check=True)
+    assert rel_err(as_sub.cpu().numpy(), as1[5:9].cpu().numpy()) < 1e-5
+
+
+def test_temporal_max_bit_exact(torch_cuda):
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    cams = torch.from_numpy(synth.make_low_res_cams(32, 5, 28, 28, seed=0)).cuda()
+    cams[3, 2, 0, 5, 5] = float("nan")
+    cams[4, 0, 0, 1, 1] = float("nan")
+    cams[6, 4, 0, 0, 0] = float("inf")
+    got = ops.temporal_cam_max(cams)
+    want = cams[:, 0]
+    for t in range(1, cams.shape[1]):
+        want = torch.maximum(want, cams[:, t])          # the chain in wsol_loader.py:591-600
+    assert got.shape == want.shape
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    assert torch.equal(torch.isnan(got), torch.isnan(want))

@@ -1,0 +1,169 @@
+"""CPU suite, part 2: host logic and the drop-in boundary (no GPU, no compute calls).
+
+* the product's device header (lattice.cuh), compiled for the host, embeds pixels and steps to
+  neighbours exactly like the oracle (keys, barycentric weights bit for bit);
+* libtcamcrf.so loads here and exports every symbol include/tcamcrf.h declares;
+* argument validation of the C ABI and of the python drop-in modules.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from tcam_wsol_video_b200 import _lib, synth
+
+
+def _features(img, h, w, srgb, sxy, color_dim=0):
+    p = h * w
+    if color_dim:
+        return np.ascontiguousarray((img.reshape(img.shape[0], -1)[:color_dim].T / np.float32(srgb)).astype(np.float32))
+    f = np.zeros((p, 5), np.float32)
+    rows, cols = np.divmod(np.arange(p), w)
+    f[:, 0] = cols.astype(np.float32) / np.float32(sxy)
+    f[:, 1] = rows.astype(np.float32) / np.float32(sxy)
+    for c in range(3):
+        f[:, 2 + c] = img[c].reshape(-1) / np.float32(srgb)
+    return f
+
+
+def _embed(harness, feats, d, scale):
+    n = feats.shape[0]
+    coords = np.zeros((n, d + 1, d), np.int16)
+    bary = np.zeros((n, d + 1), np.float32)
+    packed = np.zeros((n, d + 1), np.uint64)
+    fp = ctypes.POINTER(ctypes.c_float)
+    bad = harness.harness_embed(d, feats.ctypes.data_as(fp), n, scale.ctypes.data_as(fp),
+                                coords.ctypes.data_as(ctypes.c_void_p), bary.ctypes.data_as(fp),
+                                packed.ctypes.data_as(ctypes.c_void_p))
+    return bad, coords, bary, packed
+
+
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+@pytest.mark.parametrize("d,sig", [(5, (15.0, 100.0)), (5, (3.0, 8.0)), (3, (15.0, 0.0)), (1, (15.0, 0.0))])
+def test_device_embedding_matches_oracle(harness, oracle_mod, kind, d, sig):
+    h, w = 36, 44
+    srgb, sxy = sig
+    img = synth.make_images(1, h, w, kind, seed=11)[0]
+    if d == 5:
+        feats = _features(img, h, w, srgb, sxy)
+        L = oracle_mod.port_lattice_bilateral(img, h, w, srgb, sxy)
+    else:
+        feats = _features(img, h, w, srgb, sxy, color_dim=d)
+        L = oracle_mod.port_lattice_color(img, h, w, srgb, d)
+    scale = oracle_mod.port_scale_factors(d)
+    bad, coords, bary, packed = _embed(harness, feats, d, scale)
+    assert bad == 0
+    n = h * w
+    assert np.array_equal(L.keys[L.offset[:n]], coords)      # same lattice vertices, coordinate by coordinate
+    assert np.array_equal(L.bary[:n], bary)                    # bit-exact barycentric weights
+    uniq, first = np.unique(packed.reshape(-1), return_index=True)
+    assert len(uniq) == L.m                                    # packing is injective on the vertices
+    # neighbour stepping on packed keys == +-1 / -+d on the coordinates (permutohedral.cpp:285-290)
+    kc = coords.reshape(-1, d)[first]
+    m = len(uniq)
+    n1 = np.zeros((d + 1, m, d), np.int16)
+    n2 = np.zeros_like(n1)
+    assert harness.harness_neighbours(d, uniq.ctypes.data_as(ctypes.c_void_p), m,
+                                      n1.ctypes.data_as(ctypes.c_void_p), n2.ctypes.data_as(ctypes.c_void_p)) == 0
+    for j in range(d + 1):
+        e1, e2 = kc - 1, kc + 1
+        if j < d:
+            e1[:, j] = kc[:, j] + d
+            e2[:, j] = kc[:, j] - d
+        assert np.array_equal(e1, n1[j]) and np.array_equal(e2, n2[j])
+
+
+def test_key_range_is_reported(harness, oracle_mod):
+    """Features far outside the packed-key range must be flagged, never wrapped silently."""
+    d = 5
+    bits = harness.harness_field_bits(d)
+    assert bits == 12
+    scale = oracle_mod.port_scale_factors(d)
+    feats = np.zeros((2, d), np.float32)
+    feats[1, 4] = 1e6
+    bad, _, _, _ = _embed(harness, feats, d, scale)
+    assert bad == 1
+    for dd, expect in ((1, 20), (2, 20), (3, 20), (4, 15), (6, 10)):
+        assert harness.harness_field_bits(dd) == expect
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "tcamcrf.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(\w+)\s*\([^;{]*\)\s*;", header))
+    declared = {d for d in declared if not d.isupper()}
+    assert declared, "no prototypes parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tcamcrf.h but not exported"
+    assert lib.tcamcrf_version() == 100
+
+
+def test_workspace_sizing_and_argument_validation():
+    lib = _lib.load()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    small = lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 1, 2, 224, 224)
+    big = lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 32, 2, 224, 224)
+    assert 0 < small < big
+    # chunking bounds the workspace: 256 frames need no more than the default chunk of 64
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 256, 2, 224, 224) == \
+        lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 64, 2, 224, 224)
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 0, 2, 224, 224) == 0
+    assert b"positive" in lib.tcamcrf_last_error()
+    bad = _lib.make_config(_lib.FEAT_XY_RGB, 5, 15.0, 100.0)   # d = 7 > 6
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(bad), 1, 2, 8, 8) == 0
+    assert b"dimension" in lib.tcamcrf_last_error()
+    bad = _lib.make_config(_lib.FEAT_COLOR, 3, 0.0)
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(bad), 1, 2, 8, 8) == 0
+    # null pointers are rejected before anything touches the device
+    assert lib.tcamcrf_filter(ctypes.byref(cfg), None, None, None, 1, 2, 8, 8, None, 0, None) == 1
+    assert lib.tcamcrf_loss_backward(None, None, None, 16, 1.0, None) == 1
+    assert lib.tcam_temporal_max(None, None, 1, 1, 1, None) == 1
+
+
+def test_dropin_modules_validate_like_the_swig_typemaps():
+    from tcam_wsol_video_b200 import bilateralfilter as bf
+    from tcam_wsol_video_b200 import colorbilateralfilter as cbf
+    img = np.zeros(3 * 4 * 4, np.float32)
+    seg = np.zeros(2 * 4 * 4, np.float32)
+    out = np.zeros_like(seg)
+    with pytest.raises(TypeError):
+        bf.bilateralfilter_batch(img.astype(np.float64), seg, out, 1, 2, 4, 4, 15.0, 100.0)
+    with pytest.raises(TypeError):
+        bf.bilateralfilter_batch(img.reshape(3, 16), seg, out, 1, 2, 4, 4, 15.0, 100.0)
+    with pytest.raises(TypeError):
+        cbf.colorbilateralfilter_batch(img, seg[::2], out, 1, 1, 4, 4, 15.0, 3)
+    with pytest.raises(ValueError):
+        bf.bilateralfilter_batch(img, seg, out, 2, 2, 4, 4, 15.0, 100.0)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a B200 every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tcam_wsol_video_b200 import bilateralfilter as bf
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    img = np.zeros(3 * 4 * 4, np.float32)
+    seg = np.zeros(2 * 4 * 4, np.float32)
+    out = np.zeros_like(seg)
+    with pytest.raises(_lib.TcamCrfError):
+        bf.bilateralfilter_batch(img, seg, out, 1, 2, 4, 4, 15.0, 100.0)
+    loss = DenseCRFLoss(weight=1e-7, sigma_rgb=15.0, sigma_xy=100.0, scale_factor=1.0)
+    with pytest.raises(_lib.TcamCrfError):
+        loss(images=torch.zeros(1, 3, 4, 4), segmentations=torch.zeros(1, 2, 4, 4))
+    assert "sigma_rgb=15.0, sigma_xy=100.0, weight=1e-07, scale_factor=1.0" == loss.extra_repr()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tcam_wsol_video_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "liboracle" not in text and "_ref/" not in text, f
