@@ -173,7 +173,7 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     pl.chunk = chunk < N ? chunk : N;
     float load = cfg->hash_load > 0.f ? cfg->hash_load : 0.6f;
     if (load > 0.95f) load = 0.95f;
-    const double worst = (double)(D + 1) * pl.P;  // every pixel contributes d+1 distinct vertices
+    const double worst = (double)(D + 1) * (pl.P + 1);  // every pixel (+ the ghost) contributes d+1 distinct vertices
     unsigned long long need = (unsigned long long)(worst / load) + 1;
     unsigned long long slots = 1024;
     while (slots < need) slots <<= 1;
@@ -185,7 +185,8 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     if (pl.pool > 0x7fffff00ll) return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
     if ((unsigned long long)pl.slots * pl.chunk > 0x7fffff00ull)
         return fail(TCAMCRF_ERR_INVALID, "hash tables too large; lower chunk_frames");
-    pl.blocks_per_frame = (pl.P + kThreads - 1) / kThreads;
+    // + 1: the ghost pixel that stands for the reference's zero-feature padding (see build_kernel)
+    pl.blocks_per_frame = (pl.P + 1 + kThreads - 1) / kThreads;
 
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -252,6 +253,12 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
     const int n = blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
     const bool valid = pix < p.P;
+    // The reference embeds pixels four at a time and also inserts the zero-feature padding pixels of the
+    // last partial block (permutohedral.cpp:173,238-251).  Those vertices are never splatted to, but they
+    // exist, pick up values during the blur and hand them on -- so they change the result.  All padding
+    // pixels share one feature vector, hence one ghost pixel per frame reproduces them.
+    const bool ghost = (pix == p.P) && (p.P & 3) != 0;
+    const bool active = valid || ghost;
     const int lane = threadIdx.x & 31;
 
     int slot[D + 1];
@@ -260,10 +267,13 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
     unsigned int wonmask = 0;
     bool ok = true;
 
-    if (valid) {
+    if (active) {
         float f[D];
         const size_t img0 = (size_t)n * p.stride_planes * p.P + pix;
-        if (p.feat == TCAMCRF_FEAT_XY_RGB) {
+        if (ghost) {
+#pragma unroll
+            for (int c = 0; c < D; c++) f[c] = 0.0f;
+        } else if (p.feat == TCAMCRF_FEAT_XY_RGB) {
             const int row = pix / p.W, col = pix - row * p.W;
             f[0] = __fdiv_rn((float)col, p.sigma_xy);
             if (D > 1) f[1 < D ? 1 : 0] = __fdiv_rn((float)row, p.sigma_xy);
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
         const unsigned int peers = __match_any_sync(0xffffffffu, key[r]);
         const int leader = __ffs(peers) - 1;
         int s = -1;
-        if (valid && lane == leader) {
+        if (active && lane == leader) {
             bool won;
             s = table_insert(keys, mask, key[r], won);
             if (won) wonmask |= 1u << r;

@@ -131,23 +131,28 @@ def test_lattice_structure_bit_exact(torch_cuda, oracle_mod, kind, dim, hw):
     off, bary, M, nbr = _debug_lattice(cfg, img_in, h, w)
     p = h * w
     d = L.d
-    # the oracle also inserts the reference's zero-feature padding pixels when P % 4 != 0; those vertices
-    # are never splatted to, so compare on the vertices real pixels touch
+    # both sides also hold the vertices of the reference's zero-feature padding pixels when P % 4 != 0
+    # (permutohedral.cpp:173,238-251); no real pixel points at those that are padding-only
+    assert M == L.m
     used = np.unique(L.offset[:p])
-    assert M == len(used)
     assert np.array_equal(bary, L.bary[:p])                     # bit-exact weights
-    # ids are a relabelling: the map oracle id -> gpu id must be a bijection
+    # ids are a relabelling: the map oracle id -> gpu id must be a bijection on the vertices pixels touch
     fwd = np.full(L.m, -1, np.int64)
     fwd[L.offset[:p].ravel()] = off.ravel()
     assert np.array_equal(fwd[L.offset[:p].ravel()], off.ravel())   # consistent
     assert len(np.unique(fwd[used])) == len(used)                   # injective
-    # neighbour tables agree under the relabelling (missing stays missing; a neighbour that is only a
-    # padding vertex of the oracle has no gpu id and no value, i.e. it is "missing" on both sides)
+    gpu_used = set(fwd[used].tolist())
+    # neighbour tables agree under the relabelling; missing stays missing; a padding-only neighbour (whose
+    # relabelling is unknown) must at least exist on the gpu side and not be one of the pixel-touched vertices
     ext = np.concatenate([fwd, [-1]])
     for j in range(d + 1):
-        want = ext[L.nbr[j][used]]                                  # [len(used), 2] in gpu ids
+        want_ref = L.nbr[j][used]                                   # [len(used), 2] in oracle ids
+        want = ext[want_ref]
         got = nbr[j][fwd[used]]
-        assert np.array_equal(want, got), f"axis {j}"
+        known = (want_ref < 0) | (want >= 0)
+        assert np.array_equal(want[known], got[known]), f"axis {j}"
+        for g in got[~known].ravel().tolist():
+            assert g >= 0 and g not in gpu_used, f"axis {j}: padding-only neighbour"
 
 
 # ---------------------------------------------------------------------------
