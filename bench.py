@@ -65,6 +65,7 @@ def stage_bytes(P: int, d: int, K: int, M: float):
         "slice": 8 * dp1 * P + 4 * K * M + 4 * K * P,   # offset + bary in; value table in; AS out
         "loss": 0,
         "backward": 4 * K * P,                     # gradient out
+        "prepare": 0,                              # table clear: not algorithmic traffic
     }
 
 

@@ -67,7 +67,8 @@ typedef struct tcamcrf_config {
                                 batch functions hard-code 3 (bilateralfilter.cpp:51, colorbilateralfilter.cpp:50) */
     float sigma_rgb;
     float sigma_xy;    /* ignored for TCAMCRF_FEAT_COLOR */
-    float hash_load;   /* worst-case load factor the per-frame table is sized for; 0 -> default (0.6) */
+    float hash_load;   /* load factor the primary table tier would have at 1.2 vertices per pixel; 0 -> default (0.25).
+                          Larger lattices spill into a worst-case-sized overflow tier, so any value is safe. */
     float pool_factor; /* vertex pool size as a fraction of the worst case (d+1)*H*W per frame; 0 -> 1.0 */
     int chunk_frames;  /* frames processed per pass (bounds the workspace); 0 -> default (64) */
 } tcamcrf_config;
@@ -135,8 +136,9 @@ int tcamcrf_loss_fwd_bwd_host(const tcamcrf_config *cfg, const float *images_hos
 
 /* ---- measurement hooks (bench.py) ----
  * Stage timing brackets every pipeline stage with CUDA events on the caller's stream (not capture-safe while
- * enabled).  Stages: 0 build, 1 neighbour, 2 splat, 3 blur (d+1 launches), 4 slice, 5 loss reduce/finish, 6 backward. */
-#define TCAMCRF_STAGES 7
+ * enabled).  Stages: 0 build, 1 neighbour, 2 splat, 3 blur (d+1 launches), 4 slice, 5 loss reduce/finish, 6 backward,
+ * 7 prepare (table clear). */
+#define TCAMCRF_STAGES 8
 void tcamcrf_profile_enable(int on);
 /* Waits for the recorded events; fills accumulated milliseconds and kernel launches per stage. */
 int tcamcrf_profile_read(double *ms, long long *launches, int reset);

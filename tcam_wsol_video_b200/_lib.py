@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 FEAT_XY_RGB = 0
 FEAT_COLOR = 1
 
-STAGES = ("build", "neighbour", "splat", "blur", "slice", "loss", "backward")
+STAGES = ("build", "neighbour", "splat", "blur", "slice", "loss", "backward", "prepare")
 
 DEV_TABLE_FULL = 1
 DEV_POOL_FULL = 2
@@ -71,7 +71,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into csrc/libtcamcrf.so for sm_100a (cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("TCAMCRF_NVCC_EXTRA", "").split()   # e.g. -DTCAMCRF_NBR_U=4 for tuning sweeps
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(" ".join(cmd))

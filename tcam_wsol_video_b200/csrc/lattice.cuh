@@ -73,6 +73,24 @@ struct KeyCodec {
             k |= ((unsigned long long)(unsigned)(q[i] + kBias) & kFieldMask) << (kRemBits + i * kFieldBits);
         return k;
     }
+    // The d+1 vertices of the simplex of a point: remainder r has quotients z[i] - [rank[i] + r > D]
+    // (the canonical simplex, permutohedral.cpp:148-153,247).  Packed once for r = 0 and then derived by
+    // subtracting the field units of the coordinates that have crossed, instead of re-packing d fields.
+    __device__ static void pack_simplex(const int (&z)[D + 1], const int (&rank)[D + 1],
+                                        unsigned long long (&key)[D + 1])
+    {
+        int q0[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) q0[i] = z[i];
+        const unsigned long long base = pack(q0, 0);   // rank[i] + 0 > D never holds
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            unsigned long long k = base + (unsigned long long)r;
+#pragma unroll
+            for (int i = 0; i < D; i++) k -= (rank[i] + r > D) ? unit(i) : 0ull;
+            key[r] = k;
+        }
+    }
     // lattice coordinate i of a packed key (for debugging / tests)
     __host__ __device__ static int coord(unsigned long long key, int i)
     {
@@ -103,15 +121,15 @@ struct KeyCodec {
     }
 };
 
-// murmur3 finaliser: the table index is the low bits of this
-__device__ __forceinline__ unsigned int hash_key(unsigned long long k)
+// murmur3 finaliser; the low word indexes the primary tier, the high word the overflow tier
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k)
 {
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdull;
     k ^= k >> 33;
     k *= 0xc4ceb9fe1a85ec53ull;
     k ^= k >> 33;
-    return (unsigned int)k;
+    return k;
 }
 
 struct EmbedConsts {
@@ -185,15 +203,15 @@ __device__ __forceinline__ bool embed_point(const float (&f)[D], const EmbedCons
 
     // barycentric weights (:222-240): with v sorted by rank,
     //   b[t] = v[rank = D-t] - v[rank = D-t+1],  b[0] += 1 + b[D+1]
-    float vs[D + 2];
+    float v[D + 1], vs[D + 1];
 #pragma unroll
-    for (int t = 0; t <= D + 1; t++) vs[t] = 0.0f;
+    for (int i = 0; i <= D; i++) v[i] = __fmul_rn(__fsub_rn(el[i], __fmul_rn((float)z[i], dp1)), inv_dp1);
 #pragma unroll
-    for (int i = 0; i <= D; i++) {
-        const float v = __fmul_rn(__fsub_rn(el[i], __fmul_rn((float)z[i], dp1)), inv_dp1);
+    for (int t = 0; t <= D; t++) {
+        float sel = 0.0f;
 #pragma unroll
-        for (int t = 0; t <= D; t++)
-            if (rank[i] == t) vs[t] = v;
+        for (int i = 0; i <= D; i++) sel = (rank[i] == t) ? v[i] : sel;
+        vs[t] = sel;
     }
 #pragma unroll
     for (int t = 1; t <= D; t++) bary[t] = __fsub_rn(vs[D - t], vs[D - t + 1]);
@@ -203,43 +221,117 @@ __device__ __forceinline__ bool embed_point(const float (&f)[D], const EmbedCons
 }
 
 #if defined(__CUDACC__)
-// Inserts `key` into the open-addressing table keys[0..mask] (linear probing).
-// Returns the slot, or -1 when the table is full.  `won` tells whether this call
-// created the entry.  Loads bypass L1 (ld.global.cg): the table is written
-// concurrently by other SMs, and a stale EMPTY would only cost one extra CAS.
-__device__ __forceinline__ int table_insert(unsigned long long *keys, unsigned int mask, unsigned long long key,
-                                            bool &won)
+// ---------------------------------------------------------------------------
+// Two-tier open-addressing table (one per frame), 16-byte entries {key, id}.
+//
+//   primary tier : `slots1` entries, sized for the lattice sizes real frames produce (a few
+//                  vertices per pixel at most) so that the tables of the frames in flight stay in
+//                  the 126 MB L2.  A key probes at most `window` consecutive slots here.
+//   overflow tier: `slots2` entries, sized for the worst case (every pixel contributes d+1 distinct
+//                  vertices).  Only keys whose primary window is full of other keys go here, so
+//                  it is normally never touched -- and never needs clearing (see prepare_kernel).
+//
+// Occupied slots never change, so "window full of other keys" is a stable property: every thread
+// that handles the same key takes the same decision and finds the same entry.
+// Replaces HashTable::find / grow (permutohedral.cpp:18-41,67-95): no rehash is ever needed.
+// ---------------------------------------------------------------------------
+struct __align__(16) Entry {
+    unsigned long long key;
+    int id;   // dense vertex id, written by the thread that created the entry
+    int pad;
+};
+
+struct TableGeom {
+    unsigned int slots1, slots2;  // powers of two
+    unsigned int window;          // max probes in the primary tier
+};
+
+__device__ __forceinline__ unsigned long long load_key_cg(const Entry *e)
 {
-    unsigned int h = hash_key(key) & mask;
+    return __ldcg(&e->key);  // bypass L1: other SMs insert concurrently
+}
+
+// Continues the insertion of `key` into the frame table `tab` (primary tier at [0, slots1), overflow at
+// [slots1, slots1+slots2)) from primary slot `h`, after `probes` primary slots have already been rejected;
+// `cur` holds the key read from slot `h`.  Callers run the first probes of all their keys in lock step
+// (build_kernel) so that the round trips overlap, and come here only for the stragglers.
+// Returns the entry index, or -1 when both tiers are full.  `won`: this call created the entry.
+// `spilled`: the overflow tier was used.
+__device__ __forceinline__ int table_insert_from(Entry *tab, const TableGeom g, unsigned long long key,
+                                                 unsigned int h, unsigned int probes, unsigned long long cur,
+                                                 bool &won, bool &spilled)
+{
     won = false;
-    for (unsigned int probes = 0; probes <= mask; probes++) {
-        unsigned long long cur = __ldcg(keys + h);
+    spilled = false;
+    const unsigned int mask1 = g.slots1 - 1;
+    for (; probes < g.window; probes++) {
         if (cur == key) return (int)h;
         if (cur == kEmptyKey) {
-            cur = atomicCAS(keys + h, kEmptyKey, key);
+            cur = atomicCAS(&tab[h].key, kEmptyKey, key);
             if (cur == kEmptyKey) {
                 won = true;
                 return (int)h;
             }
             if (cur == key) return (int)h;
         }
-        h = (h + 1) & mask;
+        h = (h + 1) & mask1;
+        cur = load_key_cg(tab + h);
+    }
+    spilled = true;
+    Entry *ov = tab + g.slots1;
+    const unsigned int mask2 = g.slots2 - 1;
+    h = (unsigned int)(hash_key(key) >> 32) & mask2;
+    for (probes = 0; probes <= mask2; probes++) {
+        cur = load_key_cg(ov + h);
+        if (cur == key) return (int)(g.slots1 + h);
+        if (cur == kEmptyKey) {
+            cur = atomicCAS(&ov[h].key, kEmptyKey, key);
+            if (cur == kEmptyKey) {
+                won = true;
+                return (int)(g.slots1 + h);
+            }
+            if (cur == key) return (int)(g.slots1 + h);
+        }
+        h = (h + 1) & mask2;
     }
     return -1;
 }
 
-// Finds `key`; returns the slot or -1.
-__device__ __forceinline__ int table_lookup(const unsigned long long *__restrict__ keys, unsigned int mask,
-                                            unsigned long long key)
+// Continues a lookup from primary slot `h` whose entry `e` has already been loaded (`probes` slots rejected
+// before it).  Returns the vertex id or -1.
+__device__ __forceinline__ int table_lookup_from(const Entry *__restrict__ tab, const TableGeom g,
+                                                 unsigned long long key, unsigned int h, unsigned int probes,
+                                                 uint4 e)
 {
-    unsigned int h = hash_key(key) & mask;
-    for (unsigned int probes = 0; probes <= mask; probes++) {
-        const unsigned long long cur = __ldg(keys + h);
-        if (cur == key) return (int)h;
+    const unsigned int mask1 = g.slots1 - 1;
+    for (; probes < g.window; probes++) {
+        const unsigned long long cur = ((unsigned long long)e.y << 32) | e.x;
+        if (cur == key) return (int)e.z;
         if (cur == kEmptyKey) return -1;
-        h = (h + 1) & mask;
+        h = (h + 1) & mask1;
+        e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
+    }
+    const Entry *ov = tab + g.slots1;
+    const unsigned int mask2 = g.slots2 - 1;
+    h = (unsigned int)(hash_key(key) >> 32) & mask2;
+    for (probes = 0; probes <= mask2; probes++) {
+        e = __ldg(reinterpret_cast<const uint4 *>(ov + h));
+        const unsigned long long cur = ((unsigned long long)e.y << 32) | e.x;
+        if (cur == key) return (int)e.z;
+        if (cur == kEmptyKey) return -1;
+        h = (h + 1) & mask2;
     }
     return -1;
+}
+
+// Finds `key` (table complete, read-only); returns its vertex id or -1.  One 16-byte load per probe
+// returns both the key and the id.
+__device__ __forceinline__ int table_lookup(const Entry *__restrict__ tab, const TableGeom g,
+                                            unsigned long long key)
+{
+    const unsigned int h = (unsigned int)hash_key(key) & (g.slots1 - 1);
+    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
+    return table_lookup_from(tab, g, key, h, 0, e);
 }
 #endif  // __CUDACC__
 

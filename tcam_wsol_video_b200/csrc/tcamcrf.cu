@@ -2,14 +2,17 @@
 //
 // Pipeline for one chunk of frames (all launches on the caller's stream):
 //
-//   memset keys=EMPTY, ctrl=0
+//   prepare_kernel       clears the primary tier of the frame tables (and the overflow
+//                        tier only if the previous use spilled into it), zeroes counters
 //   build_kernel<D>      per pixel: features -> embedding -> d+1 packed keys ->
-//                        warp-deduplicated insert into the frame's table;
-//                        block-aggregated allocation of dense vertex ids
-//   neighbour_kernel<D>  per (vertex, axis): 2 table lookups -> nbr[axis][v];
-//                        also zeroes the value buffer up to the vertex count
-//   splat_kernel<V>      per pixel: slot -> dense id (kept for slice), vector
-//                        RED.ADD of w * seg[k] into values[id][0..K)
+//                        warp-deduplicated insert into the frame's two-tier table
+//                        (all first probes issued before any is consumed);
+//                        block-aggregated allocation of dense, per-frame-contiguous ids
+//   vertex_init_kernel   zeroes the value rows of the vertices in use, presets links to "missing"
+//   neighbour_kernel<D>  per (vertex, axis): ONE table lookup (the n1 neighbour); the
+//                        symmetric n2 link is written from the other side
+//   splat_kernel<V>      per pixel: entry -> dense id (kept for slice), vector
+//                        RED.ADD of w * seg[k] into values[id][0..Kp)
 //   blur_kernel<V> x(d+1) per (vertex, k-vector): new = old + 0.5*(old[n1]+old[n2])
 //   slice_kernel<V>      per pixel: AS[k] = sum_r (bary_r*alpha) * values[id_r][k];
 //                        block partial of seg . AS
@@ -67,7 +70,7 @@ static int fail(int code, const char *fmt, ...)
 // ---------------------------------------------------------------------------
 // optional per-stage timing (CUDA events on the caller's stream) + launch counter
 // ---------------------------------------------------------------------------
-enum Stage { kStBuild = 0, kStNeighbour, kStSplat, kStBlur, kStSlice, kStLoss, kStBackward, kStCount };
+enum Stage { kStBuild = 0, kStNeighbour, kStSplat, kStBlur, kStSlice, kStLoss, kStBackward, kStPrepare, kStCount };
 static_assert(kStCount == TCAMCRF_STAGES, "stage list and header disagree");
 
 struct Profiler {
@@ -126,20 +129,37 @@ struct StageScope {
 // workspace layout
 // ---------------------------------------------------------------------------
 constexpr int kThreads = 256;
-constexpr int kCtrlInts = 64;
-// ctrl[0] = device status bits, ctrl[1] = vertex pool counter (this chunk),
-// ctrl[2] = vertex count of the last finished chunk
-constexpr int kCtrlStatus = 0, kCtrlCount = 1, kCtrlLastCount = 2;
+
+// tuning knobs (items a thread keeps in flight per loop iteration); see profiles/README.md for the sweeps
+#ifndef TCAMCRF_NBR_U
+#define TCAMCRF_NBR_U 1
+#endif
+#ifndef TCAMCRF_BLUR_U
+#define TCAMCRF_BLUR_U 1
+#endif
+
+// ctrl words (ints).  [0,16) are reset by the host at the start of every call; MAGIC/DIRTY persist
+// with the workspace; per-frame vertex counters follow at kCtrlCounts.
+constexpr int kCtrlStatus = 0;      // TCAMCRF_DEV_* bits
+constexpr int kCtrlLastCount = 1;   // vertices of the last chunk (sum over frames)
+constexpr int kCtrlDirtyNew = 2;    // the build of the current chunk spilled into the overflow tier
+constexpr int kCtrlResetInts = 16;
+constexpr int kCtrlMagic = 16;      // signature of the plan that last initialised the tables
+constexpr int kCtrlDirty = 17;      // overflow tier holds keys (must be cleared before reuse)
+constexpr int kCtrlCounts = 32;     // [chunk] vertices per frame
 
 struct Plan {
-    int D, K, H, W, P;
+    int D, K, Kp, H, W, P;
     int chunk;              // frames per pass
-    unsigned int slots;     // table slots per frame (power of two)
-    long long pool;         // vertex pool entries per chunk
+    TableGeom geom;         // per-frame table geometry
+    unsigned int slots;     // geom.slots1 + geom.slots2
+    int stride;             // vertex ids per frame (ids of frame n: [n*stride, n*stride + M_n))
+    long long pool;         // chunk * stride
     int blocks_per_frame;   // pixel blocks per frame
+    int sig;                // plan signature stored in the workspace
     // byte offsets into the workspace
-    size_t off_ctrl, off_acc, off_partial, off_keys, off_slot_id, off_offset, off_bary, off_vkey, off_vframe,
-        off_nbr, off_val0, off_val1, total;
+    size_t off_ctrl, off_acc, off_partial, off_table, off_offset, off_bary, off_vkey, off_nbr, off_val0, off_val1,
+        total;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -151,6 +171,13 @@ static int feature_dim(const tcamcrf_config *cfg)
     if (cfg->feat == TCAMCRF_FEAT_XY_RGB) return 2 + cfg->channels;
     if (cfg->feat == TCAMCRF_FEAT_COLOR) return cfg->channels;
     return -1;
+}
+
+static unsigned int pow2_at_least(double need, unsigned int lo)
+{
+    unsigned long long v = lo;
+    while ((double)v < need) v <<= 1;
+    return v > (1ull << 30) ? 0u : (unsigned int)v;
 }
 
 static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan &pl)
@@ -166,27 +193,37 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
         return fail(TCAMCRF_ERR_INVALID, "sigmas must be positive");
     pl.D = D;
     pl.K = K;
+    pl.Kp = K <= 2 ? K : (K + 3) / 4 * 4;  // value rows padded to whole float4s
     pl.H = H;
     pl.W = W;
     pl.P = H * W;
     int chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 64;
+    if (chunk > 256) chunk = 256;  // kMaxChunk: the vertex kernels keep a per-frame prefix sum in shared memory
     pl.chunk = chunk < N ? chunk : N;
-    float load = cfg->hash_load > 0.f ? cfg->hash_load : 0.6f;
-    if (load > 0.95f) load = 0.95f;
-    const double worst = (double)(D + 1) * (pl.P + 1);  // every pixel (+ the ghost) contributes d+1 distinct vertices
-    unsigned long long need = (unsigned long long)(worst / load) + 1;
-    unsigned long long slots = 1024;
-    while (slots < need) slots <<= 1;
-    if (slots > (1ull << 30)) return fail(TCAMCRF_ERR_INVALID, "hash table too large");
-    pl.slots = (unsigned int)slots;
+    // every pixel (+ the ghost pixel) contributes at most d+1 distinct vertices
+    const double worst = (double)(D + 1) * (pl.P + 1);
+    // primary tier: hash_load is the load it would have with 1.2 vertices per pixel (iid-noise frames at
+    // 224^2 have 1.12, natural frames ~0.06); overflow tier: worst case at load 0.75
+    float load = cfg->hash_load > 0.f ? cfg->hash_load : 0.25f;
+    pl.geom.slots1 = pow2_at_least(1.2 * (pl.P + 1) / load, 256);
+    pl.geom.slots2 = pow2_at_least(worst / 0.75, 256);
+    if (!pl.geom.slots1 || !pl.geom.slots2) return fail(TCAMCRF_ERR_INVALID, "hash table too large");
+    pl.geom.window = pl.geom.slots1 < 128 ? pl.geom.slots1 : 128;
+    pl.slots = pl.geom.slots1 + pl.geom.slots2;
     float pf = cfg->pool_factor > 0.f ? cfg->pool_factor : 1.0f;
     if (pf > 1.f) pf = 1.f;
-    pl.pool = (long long)(worst * pf * pl.chunk) + 32;
+    pl.stride = ((int)(worst * pf) + 32 + 31) / 32 * 32;
+    pl.pool = (long long)pl.stride * pl.chunk;
     if (pl.pool > 0x7fffff00ll) return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
     if ((unsigned long long)pl.slots * pl.chunk > 0x7fffff00ull)
         return fail(TCAMCRF_ERR_INVALID, "hash tables too large; lower chunk_frames");
     // + 1: the ghost pixel that stands for the reference's zero-feature padding (see build_kernel)
     pl.blocks_per_frame = (pl.P + 1 + kThreads - 1) / kThreads;
+    unsigned int sig = 0x9e3779b9u;
+    for (unsigned int v : {(unsigned)D, (unsigned)pl.chunk, pl.geom.slots1, pl.geom.slots2, (unsigned)pl.stride,
+                           (unsigned)pl.Kp, (unsigned)pl.P})
+        sig = (sig ^ v) * 0x01000193u + 0x7f4a7c15u;
+    pl.sig = (int)(sig | 1u);
 
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -194,18 +231,16 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
         o = align_up(o + bytes, 256);
         return at;
     };
-    pl.off_ctrl = take(kCtrlInts * sizeof(int));
+    pl.off_ctrl = take((size_t)(kCtrlCounts + pl.chunk) * sizeof(int));
     pl.off_acc = take(4 * sizeof(double));
     pl.off_partial = take((size_t)pl.chunk * pl.blocks_per_frame * sizeof(float));
-    pl.off_keys = take((size_t)pl.chunk * pl.slots * sizeof(unsigned long long));
-    pl.off_slot_id = take((size_t)pl.chunk * pl.slots * sizeof(int));
+    pl.off_table = take((size_t)pl.chunk * pl.slots * sizeof(Entry));
     pl.off_offset = take((size_t)pl.chunk * (D + 1) * pl.P * sizeof(int));
     pl.off_bary = take((size_t)pl.chunk * (D + 1) * pl.P * sizeof(float));
     pl.off_vkey = take((size_t)pl.pool * sizeof(unsigned long long));
-    pl.off_vframe = take((size_t)pl.pool * sizeof(int));
     pl.off_nbr = take((size_t)(D + 1) * pl.pool * sizeof(int2));
-    pl.off_val0 = take((size_t)pl.pool * K * sizeof(float) + 64);
-    pl.off_val1 = take((size_t)pl.pool * K * sizeof(float) + 64);
+    pl.off_val0 = take((size_t)pl.pool * pl.Kp * sizeof(float) + 64);
+    pl.off_val1 = take((size_t)pl.pool * pl.Kp * sizeof(float) + 64);
     pl.total = o;
     return TCAMCRF_OK;
 }
@@ -215,17 +250,17 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
 // ---------------------------------------------------------------------------
 struct BuildParams {
     const void *images;     // [N, stride_planes, P] float or u8
-    unsigned long long *keys;
-    int *slot_id;
-    int *offset;            // [n][r][p] : global slot index (n*slots + h)
+    Entry *table;           // [n][slots1 + slots2]
+    int *offset;            // [n][r][p] : global entry index (n*slots + s)
     float *bary;            // [n][r][p]
-    unsigned long long *vkey;
-    int *vframe;
+    unsigned long long *vkey;   // [pool] key of each vertex
     int *ctrl;
     int P, W;
     int stride_planes, channels, feat;
+    TableGeom geom;
     unsigned int slots;
-    int pool;
+    int stride;             // ids per frame
+    long long pool;
     float sigma_rgb, sigma_xy;
     EmbedConsts ec;
 };
@@ -241,6 +276,36 @@ template <>
 __device__ __forceinline__ float load_pixel<uint8_t>(const void *base, size_t idx)
 {
     return (float)__ldg((const uint8_t *)base + idx);
+}
+
+// Clears the tables of `nc` frames: always the primary tier, the overflow tier only when the workspace is
+// new (magic mismatch) or the previous use spilled into it.  Also zeroes the per-frame vertex counters.
+__global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int nc, int chunk, TableGeom geom,
+                                                           int sig)
+{
+    const bool full = (ctrl[kCtrlMagic] != sig) || (ctrl[kCtrlDirty] != 0);
+    const unsigned int slots = geom.slots1 + geom.slots2;
+    const long long n_primary = (long long)nc * geom.slots1;
+    // the overflow tiers of ALL frames of the workspace are cleared together: the dirty flag is per workspace
+    const long long total = n_primary + (full ? (long long)chunk * geom.slots2 : 0);
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const uint4 empty = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);  // key EMPTY, id -1
+    uint4 *t4 = reinterpret_cast<uint4 *>(table);
+    for (long long i = tid; i < total; i += stride) {
+        long long n, s;
+        if (i < n_primary) {
+            n = i / geom.slots1;
+            s = i - n * geom.slots1;
+        } else {
+            const long long o = i - n_primary;
+            n = o / geom.slots2;
+            s = geom.slots1 + (o - n * geom.slots2);
+        }
+        t4[n * slots + s] = empty;
+    }
+    if (tid < nc) ctrl[kCtrlCounts + tid] = 0;
+    if (tid == 0) ctrl[kCtrlLastCount] = 0;
 }
 
 template <int D, typename ImgT>
@@ -293,42 +358,79 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
                 rank[i] = i;
             }
         }
-#pragma unroll
-        for (int r = 0; r <= D; r++) {
-            int q[D];
-#pragma unroll
-            for (int i = 0; i < D; i++) q[i] = z[i] - ((rank[i] + r > D) ? 1 : 0);
-            key[r] = Codec::pack(q, r);
-        }
+        Codec::pack_simplex(z, rank, key);
     } else {
 #pragma unroll
         for (int r = 0; r <= D; r++) key[r] = kEmptyKey;
     }
     if (!ok) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_KEY_RANGE);
 
-    // warp-cooperative insertion: lanes holding the same key elect one leader,
-    // only leaders touch the table, the slot is broadcast back.
-    unsigned long long *keys = p.keys + (size_t)n * p.slots;
-    const unsigned int mask = p.slots - 1;
-    bool table_full = false;
+    // Warp-cooperative insertion.  Lanes holding the same key elect one leader; only leaders touch the
+    // table and the entry index is broadcast back.  A leader probes for all the keys it leads in lock
+    // step: every round issues one load per pending key before any result is consumed, so the d+1
+    // dependent probe chains overlap instead of running one after the other.
+    Entry *tab = p.table + (size_t)n * p.slots;
+    const unsigned int mask1 = p.geom.slots1 - 1;
+    unsigned int pend = 0;
+    int leader[D + 1];
+    unsigned int hh[D + 1];
+    unsigned long long cur[D + 1];
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         const unsigned int peers = __match_any_sync(0xffffffffu, key[r]);
-        const int leader = __ffs(peers) - 1;
-        int s = -1;
-        if (active && lane == leader) {
-            bool won;
-            s = table_insert(keys, mask, key[r], won);
-            if (won) wonmask |= 1u << r;
-            if (s < 0) table_full = true;
+        leader[r] = __ffs(peers) - 1;
+        hh[r] = 0;
+        cur[r] = 0;
+        slot[r] = -1;
+        if (active && lane == leader[r]) {
+            pend |= 1u << r;
+            hh[r] = (unsigned int)hash_key(key[r]) & mask1;
+            cur[r] = load_key_cg(tab + hh[r]);
         }
-        __syncwarp();
-        s = __shfl_sync(0xffffffffu, s, leader);
-        slot[r] = s;
     }
+    constexpr int kLockstepRounds = 6;
+    int rounds = 0;
+    for (; rounds < kLockstepRounds && pend; rounds++) {
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            if (!(pend & (1u << r))) continue;
+            unsigned long long c = cur[r];
+            if (c == kEmptyKey) {
+                c = atomicCAS(&tab[hh[r]].key, kEmptyKey, key[r]);
+                if (c == kEmptyKey) {
+                    wonmask |= 1u << r;
+                    c = key[r];
+                }
+            }
+            if (c == key[r]) {
+                slot[r] = (int)hh[r];
+                pend &= ~(1u << r);
+            } else {
+                hh[r] = (hh[r] + 1) & mask1;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r <= D; r++)
+            if (pend & (1u << r)) cur[r] = load_key_cg(tab + hh[r]);
+    }
+    bool table_full = false, spilled_any = false;
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        if (pend & (1u << r)) {  // stragglers: long probe chains, overflow tier
+            bool won, spilled;
+            slot[r] = table_insert_from(tab, p.geom, key[r], hh[r], (unsigned int)rounds, cur[r], won, spilled);
+            if (won) wonmask |= 1u << r;
+            if (slot[r] < 0) table_full = true;
+            spilled_any |= spilled;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r <= D; r++) slot[r] = __shfl_sync(0xffffffffu, slot[r], leader[r]);
     if (table_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_TABLE_FULL);
+    if (spilled_any) p.ctrl[kCtrlDirtyNew] = 1;
 
-    // block-aggregated allocation of dense vertex ids: one atomic per block
+    // block-aggregated allocation of dense vertex ids: one atomic per block on the frame's counter
     const int nwin = __popc(wonmask);
     int incl = nwin;
 #pragma unroll
@@ -347,24 +449,23 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
             s_warp[w] = total;
             total += t;
         }
-        s_base = total > 0 ? atomicAdd(p.ctrl + kCtrlCount, total) : 0;
+        s_base = total > 0 ? atomicAdd(p.ctrl + kCtrlCounts + n, total) : 0;
     }
     __syncthreads();
-    int id = s_base + s_warp[warp] + incl - nwin;
+    int local = s_base + s_warp[warp] + incl - nwin;
     bool pool_full = false;
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         if (wonmask & (1u << r)) {
-            int *sid = p.slot_id + (size_t)n * p.slots + slot[r];
-            if (id < p.pool) {
-                *sid = id;
+            Entry *e = tab + slot[r];
+            if (local < p.stride) {
+                const int id = n * p.stride + local;
+                e->id = id;
                 p.vkey[id] = key[r];
-                p.vframe[id] = n;
             } else {
-                *sid = -1;
-                pool_full = true;
+                pool_full = true;  // e->id stays -1
             }
-            id++;
+            local++;
         }
     }
     if (pool_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_POOL_FULL);
@@ -380,69 +481,164 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
 }
 
 struct VertexParams {
-    const unsigned long long *keys;
-    const int *slot_id;
+    const Entry *table;
     const unsigned long long *vkey;
-    const int *vframe;
     int2 *nbr;              // [axis][pool]
-    float *values;          // zeroed here up to count*K
+    float *values;          // rows of the vertices in use are zeroed here
     int *ctrl;
+    TableGeom geom;
     unsigned int slots;
-    int pool;
-    int K;
+    int stride;
+    long long pool;
+    int Kp;
+    int sig;
 };
 
-template <int D>
-__global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams p)
+// The vertex kernels are persistent 1-D grids over the FLAT list of vertices of all frames of the chunk
+// (frame 0's vertices first, then frame 1's, ...): the per-frame counts are turned into a prefix sum in
+// shared memory once per block, and a flat index is mapped back to (frame, local vertex) by binary search.
+// Frames are therefore swept in order, and the grid works on neighbouring frames at any moment.
+constexpr int kMaxChunk = 256;
+
+__device__ __forceinline__ int load_frame_prefix(const int *ctrl, int nc, int stride, int *s_prefix)
 {
-    using Codec = KeyCodec<D>;
-    int M = p.ctrl[kCtrlCount];
-    if (M > p.pool) M = p.pool;
+    __shared__ int s_total;
+    for (int n = threadIdx.x; n < nc; n += blockDim.x) {
+        int m = ctrl[kCtrlCounts + n];
+        s_prefix[n + 1] = m > stride ? stride : m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        s_prefix[0] = 0;
+        for (int n = 0; n < nc; n++) {
+            run += s_prefix[n + 1];
+            s_prefix[n + 1] = run;
+        }
+        s_total = run;
+    }
+    __syncthreads();
+    return s_total;
+}
+
+// largest n with prefix[n] <= t  (t < prefix[nc])
+__device__ __forceinline__ int find_frame(const int *s_prefix, int nc, int t)
+{
+    int lo = 0, hi = nc;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_prefix[mid] <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// Zeroes the value rows and presets every neighbour link of the vertices in use to "missing".
+__global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int dp1, int nc)
+{
+    __shared__ int s_prefix[kMaxChunk + 1];
+    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
     const long long stride = (long long)gridDim.x * kThreads;
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const unsigned int mask = p.slots - 1;
-
-    // zero the first value buffer (vector stores; the buffer is padded)
-    {
-        const long long n4 = ((long long)M * p.K + 3) / 4;
-        float4 *v4 = reinterpret_cast<float4 *>(p.values);
-        for (long long i = tid; i < n4; i += stride) v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // value rows, one float4 at a time (Kp is 1, 2 or a multiple of 4; rows of a frame start 16-byte aligned)
+    if ((p.Kp & 3) == 0) {
+        const int q = p.Kp >> 2;
+        for (long long i = tid; i < (long long)total * q; i += stride) {
+            const int t = (int)(i / q);
+            const int n = find_frame(s_prefix, nc, t);
+            const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
+            reinterpret_cast<float4 *>(p.values + v * p.Kp)[i - (long long)t * q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (long long i = tid; i < (long long)total * p.Kp; i += stride) {
+            const int t = (int)(i / p.Kp);
+            const int n = find_frame(s_prefix, nc, t);
+            const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
+            p.values[v * p.Kp + (i - (long long)t * p.Kp)] = 0.f;
+        }
     }
-
-    const long long work = (long long)M * (D + 1);
-    for (long long i = tid; i < work; i += stride) {
-        const int j = (int)(i / M);
-        const int v = (int)(i - (long long)j * M);
-        const unsigned long long key = __ldg(p.vkey + v);
-        const size_t tbase = (size_t)__ldg(p.vframe + v) * p.slots;
-        unsigned long long k1, k2;
-        Codec::neighbour_keys(key, j, k1, k2);
-        const int s1 = table_lookup(p.keys + tbase, mask, k1);
-        const int s2 = table_lookup(p.keys + tbase, mask, k2);
-        int2 out;
-        out.x = s1 < 0 ? -1 : __ldg(p.slot_id + tbase + s1);
-        out.y = s2 < 0 ? -1 : __ldg(p.slot_id + tbase + s2);
-        p.nbr[(size_t)j * p.pool + v] = out;
+    const int2 none = make_int2(-1, -1);
+    for (long long i = tid; i < (long long)total * dp1; i += stride) {
+        const int j = (int)(i / total);
+        const int t = (int)(i - (long long)j * total);
+        const int n = find_frame(s_prefix, nc, t);
+        const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
+        p.nbr[(size_t)j * p.pool + v] = none;
     }
-    if (tid == 0) p.ctrl[kCtrlLastCount] = M;
+}
+
+// Blur neighbours.  n1(v, j) = u  <=>  n2(u, j) = v, so ONE lookup per (vertex, axis) fills both directions;
+// every link was preset to -1 by vertex_init_kernel.  Each thread handles kU (vertex, axis) items at a
+// time: their key loads and first probes are issued together so the dependent round trips overlap.
+template <int D>
+__global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams p, int nc)
+{
+    using Codec = KeyCodec<D>;
+    constexpr int kU = TCAMCRF_NBR_U;
+    __shared__ int s_prefix[kMaxChunk + 1];
+    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned int mask1 = p.geom.slots1 - 1;
+    const long long work = (long long)total * (D + 1);
+    // items are ordered frame by frame (so the grid probes one or two frame tables at a time and they stay
+    // in L2), axis-major inside a frame: adjacent lanes handle adjacent vertices of one axis (coalesced key
+    // loads and link stores)
+    for (long long base = tid; base < work; base += stride * kU) {
+        int id[kU], axis[kU];
+        const Entry *tab[kU];
+        unsigned long long k1[kU];
+        unsigned int h[kU];
+        uint4 e[kU];
+        unsigned long long key[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const long long i = base + u * stride;
+            axis[u] = -1;
+            id[u] = 0;
+            key[u] = 0;
+            tab[u] = p.table;
+            if (i < work) {
+                const int n = find_frame(s_prefix, nc, (int)(i / (D + 1)));   // prefix[n]*(D+1) <= i
+                const int m = s_prefix[n + 1] - s_prefix[n];
+                const int local = (int)(i - (long long)s_prefix[n] * (D + 1));
+                axis[u] = local / m;
+                id[u] = n * p.stride + (local - axis[u] * m);
+                tab[u] = p.table + (size_t)n * p.slots;
+                key[u] = __ldg(p.vkey + id[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            unsigned long long k2;
+            Codec::neighbour_keys(key[u], axis[u] < 0 ? 0 : axis[u], k1[u], k2);
+            h[u] = (unsigned int)hash_key(k1[u]) & mask1;
+            e[u] = make_uint4(0, 0, 0, 0);
+            if (axis[u] >= 0) e[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            if (axis[u] < 0) continue;
+            const int nb = table_lookup_from(tab[u], p.geom, k1[u], h[u], 0, e[u]);
+            if (nb >= 0) {
+                int2 *row = p.nbr + (size_t)axis[u] * p.pool;
+                row[id[u]].x = nb;
+                row[nb].y = id[u];
+            }
+        }
+    }
+    if (tid == 0) {
+        p.ctrl[kCtrlLastCount] = total;
+        // hand the spill state of this chunk over to the next prepare_kernel
+        p.ctrl[kCtrlDirty] = p.ctrl[kCtrlDirtyNew];
+        p.ctrl[kCtrlDirtyNew] = 0;
+        p.ctrl[kCtrlMagic] = p.sig;
+    }
 }
 
 // vector helpers -------------------------------------------------------------
-template <int V>
-struct Vec;
-template <>
-struct Vec<1> {
-    using type = float;
-};
-template <>
-struct Vec<2> {
-    using type = float2;
-};
-template <>
-struct Vec<4> {
-    using type = float4;
-};
-
 __device__ __forceinline__ void red_add(float *addr, const float (&v)[1]) { atomicAdd(addr, v[0]); }
 __device__ __forceinline__ void red_add(float *addr, const float (&v)[2])
 {
@@ -485,13 +681,14 @@ __device__ __forceinline__ void store_vec(float *addr, const float (&v)[V])
 struct PixelParams {
     const float *segs;      // [n][K][P]
     float *as_out;          // [n][K][P]
-    int *offset;            // [n][r][P]; slot on entry to splat, dense id afterwards
+    int *offset;            // [n][r][P]; entry index on entry to splat, dense id afterwards
     const float *bary;      // [n][r][P]
-    const int *slot_id;
-    float *values;          // [pool][K]
+    const Entry *table;
+    float *values;          // [pool][Kp]
     float *partial;         // [n][blocks_per_frame]
     const int *ctrl;
-    int P, K, pool;
+    int P, K, Kp;
+    long long pool;
     float alpha;
 };
 
@@ -507,24 +704,23 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         const int s = p.offset[base + (size_t)r * p.P];
-        int v = s < 0 ? -1 : __ldg(p.slot_id + s);
-        if (v >= p.pool) v = -1;
+        const int v = s < 0 ? -1 : __ldg(&p.table[s].id);
         id[r] = v;
         p.offset[base + (size_t)r * p.P] = v;
         w[r] = p.bary[base + (size_t)r * p.P];
     }
     const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
-    for (int k = 0; k < p.K; k += V) {
+    for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = __ldg(seg + (size_t)(k + e) * p.P);
+        for (int e = 0; e < V; e++) s[e] = (k + e < p.K) ? __ldg(seg + (size_t)(k + e) * p.P) : 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             if (id[r] < 0) continue;
             float t[V];
 #pragma unroll
             for (int e = 0; e < V; e++) t[e] = __fmul_rn(w[r], s[e]);
-            red_add(p.values + (size_t)id[r] * p.K + k, t);
+            red_add(p.values + (size_t)id[r] * p.Kp + k, t);
         }
     }
 }
@@ -534,39 +730,60 @@ struct BlurParams {
     float *dst;
     const int2 *nbr;        // this axis: [pool]
     const int *ctrl;
-    int K, pool;
+    int Kp, stride;
 };
 
+// persistent 1-D grid over the flat vertex list (see the note above load_frame_prefix); kU items per thread
+// per iteration so that the neighbour-id loads and the two gathers of several items are in flight together
 template <int V>
-__global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p)
+__global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int nc)
 {
-    int M = p.ctrl[kCtrlCount];
-    if (M > p.pool) M = p.pool;
-    const int kv = p.K / V;
-    const long long work = (long long)M * kv;
+    constexpr int kU = TCAMCRF_BLUR_U;
+    __shared__ int s_prefix[kMaxChunk + 1];
+    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
+    const int kv = p.Kp / V;
+    const long long work = (long long)total * kv;
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < work; i += stride) {
-        const int v = (int)(i / kv);
-        const int c = (int)(i - (long long)v * kv) * V;
-        const int2 nb = __ldg(p.nbr + v);
-        float own[V], a[V], b[V], out[V];
-        load_vec<V>(p.src + (size_t)v * p.K + c, own);
-        if (nb.x >= 0)
-            load_vec<V>(p.src + (size_t)nb.x * p.K + c, a);
-        else {
+    for (long long base = (long long)blockIdx.x * kThreads + threadIdx.x; base < work; base += stride * kU) {
+        size_t v[kU];
+        int c[kU];
+        int2 nb[kU];
+        bool on[kU];
 #pragma unroll
-            for (int e = 0; e < V; e++) a[e] = 0.f;
+        for (int u = 0; u < kU; u++) {
+            const long long i = base + u * stride;
+            on[u] = i < work;
+            v[u] = 0;
+            c[u] = 0;
+            nb[u] = make_int2(-1, -1);
+            if (on[u]) {
+                const int t = (int)(i / kv);
+                c[u] = (int)(i - (long long)t * kv) * V;
+                const int n = find_frame(s_prefix, nc, t);
+                v[u] = (size_t)n * p.stride + (t - s_prefix[n]);
+                nb[u] = __ldg(p.nbr + v[u]);
+            }
         }
-        if (nb.y >= 0)
-            load_vec<V>(p.src + (size_t)nb.y * p.K + c, b);
-        else {
+        float own[kU][V], a[kU][V], b[kU][V];
 #pragma unroll
-            for (int e = 0; e < V; e++) b[e] = 0.f;
+        for (int u = 0; u < kU; u++) {
+#pragma unroll
+            for (int e = 0; e < V; e++) own[u][e] = a[u][e] = b[u][e] = 0.f;
+            if (on[u]) {
+                load_vec<V>(p.src + v[u] * p.Kp + c[u], own[u]);
+                if (nb[u].x >= 0) load_vec<V>(p.src + (size_t)nb[u].x * p.Kp + c[u], a[u]);
+                if (nb[u].y >= 0) load_vec<V>(p.src + (size_t)nb[u].y * p.Kp + c[u], b[u]);
+            }
         }
-        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
 #pragma unroll
-        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
-        store_vec<V>(p.dst + (size_t)v * p.K + c, out);
+        for (int u = 0; u < kU; u++) {
+            if (!on[u]) continue;
+            float out[V];
+            // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
+#pragma unroll
+            for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[u][e], __fmul_rn(0.5f, __fadd_rn(a[u][e], b[u][e])));
+            store_vec<V>(p.dst + v[u] * p.Kp + c[u], out);
+        }
     }
 }
 
@@ -590,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
         }
         const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
         float *out = p.as_out + (size_t)n * p.K * p.P + pix;
-        for (int k = 0; k < p.K; k += V) {
+        for (int k = 0; k < p.Kp; k += V) {
             float acc[V];
 #pragma unroll
             for (int e = 0; e < V; e++) acc[e] = 0.f;
@@ -598,7 +815,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
             for (int r = 0; r <= D; r++) {
                 float val[V];
                 if (id[r] >= 0)
-                    load_vec<V>(p.values + (size_t)id[r] * p.K + k, val);
+                    load_vec<V>(p.values + (size_t)id[r] * p.Kp + k, val);
                 else {
 #pragma unroll
                     for (int e = 0; e < V; e++) val[e] = 0.f;
@@ -608,9 +825,11 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
             }
 #pragma unroll
             for (int e = 0; e < V; e++) {
-                const float o = poisoned ? __int_as_float(0x7fc00000) : acc[e];
-                out[(size_t)(k + e) * p.P] = o;
-                dot = fmaf(__ldg(seg + (size_t)(k + e) * p.P), o, dot);
+                if (k + e < p.K) {
+                    const float o = poisoned ? __int_as_float(0x7fc00000) : acc[e];
+                    out[(size_t)(k + e) * p.P] = o;
+                    dot = fmaf(__ldg(seg + (size_t)(k + e) * p.P), o, dot);
+                }
             }
         }
     }
@@ -658,7 +877,9 @@ __global__ void __launch_bounds__(kThreads) loss_backward_kernel(const float *__
                                                                  float *__restrict__ grad, size_t count, float n_norm)
 {
     const float t = __fmul_rn(-2.0f, __ldg(grad_out));
-    const size_t n4 = count / 4;
+    // vector path only when both buffers are 16-byte aligned (sub-batches of odd-sized frames are not)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(as) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+    const size_t n4 = aligned ? count / 4 : 0;
     const size_t stride = (size_t)gridDim.x * kThreads;
     const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
     const float4 *as4 = reinterpret_cast<const float4 *>(as);
@@ -717,6 +938,23 @@ static int sm_count()
 // persistent kernels: one wave of resident CTAs (8 x 256 threads per SM)
 static int persistent_grid() { return sm_count() * 8; }
 
+// Exactly one resident wave of `kernel` (what its register use allows), so that the frame-ordered sweep of
+// the vertex kernels really has all blocks on the same frame at the same time.
+template <typename Kernel>
+static int resident_grid(Kernel kernel)
+{
+    static int cached = 0;  // one instance per kernel type
+    if (cached == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+        cached = per_sm * sm_count();
+    }
+    return cached;
+}
+
 static void scale_factors(int d, EmbedConsts &ec)
 {
     // evaluated exactly like the reference: float inv_std_dev, double expression, narrowed to float
@@ -752,15 +990,14 @@ static void launch_pixel(bool splat, int V, const PixelParams &pp, dim3 grid, cu
     }
 }
 
-static void launch_blur(int V, const BlurParams &bp, cudaStream_t st)
+static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 {
-    const int grid = persistent_grid();
     if (V == 4)
-        blur_kernel<4><<<grid, kThreads, 0, st>>>(bp);
+        blur_kernel<4><<<resident_grid(blur_kernel<4>), kThreads, 0, st>>>(bp, nc);
     else if (V == 2)
-        blur_kernel<2><<<grid, kThreads, 0, st>>>(bp);
+        blur_kernel<2><<<resident_grid(blur_kernel<2>), kThreads, 0, st>>>(bp, nc);
     else
-        blur_kernel<1><<<grid, kThreads, 0, st>>>(bp);
+        blur_kernel<1><<<resident_grid(blur_kernel<1>), kThreads, 0, st>>>(bp, nc);
 }
 
 template <int D>
@@ -768,79 +1005,81 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
                        float *as_out, int nc, char *ws, bool want_loss, cudaStream_t st)
 {
     int *ctrl = (int *)(ws + pl.off_ctrl);
-    unsigned long long *keys = (unsigned long long *)(ws + pl.off_keys);
-    int *slot_id = (int *)(ws + pl.off_slot_id);
+    Entry *table = (Entry *)(ws + pl.off_table);
     int *offset = (int *)(ws + pl.off_offset);
     float *bary = (float *)(ws + pl.off_bary);
     unsigned long long *vkey = (unsigned long long *)(ws + pl.off_vkey);
-    int *vframe = (int *)(ws + pl.off_vframe);
     int2 *nbr = (int2 *)(ws + pl.off_nbr);
     float *val0 = (float *)(ws + pl.off_val0);
     float *val1 = (float *)(ws + pl.off_val1);
     float *partial = (float *)(ws + pl.off_partial);
     double *acc = (double *)(ws + pl.off_acc);
 
-    // reset the vertex counter (not the status word) and the tables of this chunk
-    CUDA_TRY(cudaMemsetAsync(ctrl + kCtrlCount, 0, sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(keys, 0xff, (size_t)nc * pl.slots * sizeof(unsigned long long), st));
-
-    BuildParams bp;
-    bp.images = images;
-    bp.keys = keys;
-    bp.slot_id = slot_id;
-    bp.offset = offset;
-    bp.bary = bary;
-    bp.vkey = vkey;
-    bp.vframe = vframe;
-    bp.ctrl = ctrl;
-    bp.P = pl.P;
-    bp.W = pl.W;
-    bp.stride_planes = cfg->image_stride_planes;
-    bp.channels = cfg->channels;
-    bp.feat = cfg->feat;
-    bp.slots = pl.slots;
-    bp.pool = (int)pl.pool;
-    bp.sigma_rgb = cfg->sigma_rgb;
-    bp.sigma_xy = cfg->sigma_xy;
-    scale_factors(D, bp.ec);
-    const dim3 pgrid(pl.blocks_per_frame, nc);
+    {
+        StageScope scope(kStPrepare, 1, st);
+        prepare_kernel<<<persistent_grid(), kThreads, 0, st>>>(table, ctrl, nc, pl.chunk, pl.geom, pl.sig);
+    }
     {
         StageScope scope(kStBuild, 1, st);
+        BuildParams bp;
+        bp.images = images;
+        bp.table = table;
+        bp.offset = offset;
+        bp.bary = bary;
+        bp.vkey = vkey;
+        bp.ctrl = ctrl;
+        bp.P = pl.P;
+        bp.W = pl.W;
+        bp.stride_planes = cfg->image_stride_planes;
+        bp.channels = cfg->channels;
+        bp.feat = cfg->feat;
+        bp.geom = pl.geom;
+        bp.slots = pl.slots;
+        bp.stride = pl.stride;
+        bp.pool = pl.pool;
+        bp.sigma_rgb = cfg->sigma_rgb;
+        bp.sigma_xy = cfg->sigma_xy;
+        scale_factors(D, bp.ec);
+        const dim3 bgrid(pl.blocks_per_frame, nc);
         if (u8)
-            launch_build<D, uint8_t>(bp, pgrid, st);
+            launch_build<D, uint8_t>(bp, bgrid, st);
         else
-            launch_build<D, float>(bp, pgrid, st);
+            launch_build<D, float>(bp, bgrid, st);
     }
+    const dim3 pgrid(pl.blocks_per_frame, nc);
 
     VertexParams vp;
-    vp.keys = keys;
-    vp.slot_id = slot_id;
+    vp.table = table;
     vp.vkey = vkey;
-    vp.vframe = vframe;
     vp.nbr = nbr;
     vp.values = val0;
     vp.ctrl = ctrl;
+    vp.geom = pl.geom;
     vp.slots = pl.slots;
-    vp.pool = (int)pl.pool;
-    vp.K = pl.K;
+    vp.stride = pl.stride;
+    vp.pool = pl.pool;
+    vp.Kp = pl.Kp;
+    vp.sig = pl.sig;
     {
-        StageScope scope(kStNeighbour, 1, st);
-        neighbour_kernel<D><<<persistent_grid(), kThreads, 0, st>>>(vp);
+        StageScope scope(kStNeighbour, 2, st);
+        vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, D + 1, nc);
+        neighbour_kernel<D><<<resident_grid(neighbour_kernel<D>), kThreads, 0, st>>>(vp, nc);
     }
 
-    const int V = (pl.K % 4 == 0) ? 4 : (pl.K % 2 == 0) ? 2 : 1;
+    const int V = (pl.Kp % 4 == 0) ? 4 : (pl.Kp % 2 == 0) ? 2 : 1;
     PixelParams pp;
     pp.segs = segs;
     pp.as_out = as_out;
     pp.offset = offset;
     pp.bary = bary;
-    pp.slot_id = slot_id;
+    pp.table = table;
     pp.values = val0;
     pp.partial = want_loss ? partial : nullptr;
     pp.ctrl = ctrl;
     pp.P = pl.P;
     pp.K = pl.K;
-    pp.pool = (int)pl.pool;
+    pp.Kp = pl.Kp;
+    pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
     {
         StageScope scope(kStSplat, 1, st);
@@ -848,21 +1087,22 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
     }
 
     float *src = val0, *dst = val1;
-    StageScope *blur_scope = new StageScope(kStBlur, D + 1, st);
-    for (int j = 0; j <= D; j++) {
-        BlurParams bl;
-        bl.src = src;
-        bl.dst = dst;
-        bl.nbr = nbr + (size_t)j * pl.pool;
-        bl.ctrl = ctrl;
-        bl.K = pl.K;
-        bl.pool = (int)pl.pool;
-        launch_blur(V, bl, st);
-        float *t = src;
-        src = dst;
-        dst = t;
+    {
+        StageScope scope(kStBlur, D + 1, st);
+        for (int j = 0; j <= D; j++) {
+            BlurParams bl;
+            bl.src = src;
+            bl.dst = dst;
+            bl.nbr = nbr + (size_t)j * pl.pool;
+            bl.ctrl = ctrl;
+            bl.Kp = pl.Kp;
+            bl.stride = pl.stride;
+            launch_blur(V, bl, nc, st);
+            float *t = src;
+            src = dst;
+            dst = t;
+        }
     }
-    delete blur_scope;
 
     pp.values = src;
     {
@@ -902,11 +1142,11 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
     if (ws_bytes < pl.total)
         return fail(TCAMCRF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
     if (((uintptr_t)workspace & 255) != 0) return fail(TCAMCRF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    if (((uintptr_t)segs & 15) || ((uintptr_t)as_out & 15))
-        return fail(TCAMCRF_ERR_INVALID, "segs/as buffers must be 16-byte aligned");
+    if (((uintptr_t)segs & 3) || ((uintptr_t)as_out & 3) || (!u8 && ((uintptr_t)images & 3)))
+        return fail(TCAMCRF_ERR_INVALID, "float buffers must be 4-byte aligned");
     char *ws = (char *)workspace;
-    // status word + loss accumulator start clean for this call
-    CUDA_TRY(cudaMemsetAsync(ws + pl.off_ctrl, 0, kCtrlInts * sizeof(int), st));
+    // status word + loss accumulator start clean for this call (MAGIC / DIRTY persist with the workspace)
+    CUDA_TRY(cudaMemsetAsync(ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(ws + pl.off_acc, 0, 4 * sizeof(double), st));
     const size_t img_elem = u8 ? 1 : 4;
     for (int n0 = 0; n0 < N; n0 += pl.chunk) {
@@ -933,7 +1173,10 @@ struct HostCtx {
     int device = -1;
     void *buf = nullptr;
     size_t cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t s_in = nullptr;     // host -> device copies
+    cudaStream_t s_out = nullptr;    // device -> host copies
+    std::vector<cudaEvent_t> events;
 };
 static HostCtx g_host;
 
@@ -941,20 +1184,39 @@ static int host_reserve(size_t bytes, char **out)
 {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (g_host.device != dev || g_host.cap < bytes) {
+    if (g_host.device != dev) {
+        for (cudaStream_t *s : {&g_host.stream, &g_host.s_in, &g_host.s_out}) {
+            if (*s) cudaStreamDestroy(*s);
+            *s = nullptr;
+        }
+        for (cudaEvent_t e : g_host.events) cudaEventDestroy(e);
+        g_host.events.clear();
         if (g_host.buf) cudaFree(g_host.buf);
         g_host.buf = nullptr;
         g_host.cap = 0;
-        if (!g_host.stream || g_host.device != dev) {
-            if (g_host.stream) cudaStreamDestroy(g_host.stream);
-            g_host.stream = nullptr;
-            CUDA_TRY(cudaStreamCreateWithFlags(&g_host.stream, cudaStreamNonBlocking));
-        }
-        CUDA_TRY(cudaMalloc(&g_host.buf, bytes));
-        g_host.cap = bytes;
         g_host.device = dev;
     }
+    for (cudaStream_t *s : {&g_host.stream, &g_host.s_in, &g_host.s_out})
+        if (!*s) CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    if (g_host.cap < bytes) {
+        if (g_host.buf) cudaFree(g_host.buf);
+        g_host.buf = nullptr;
+        g_host.cap = 0;
+        CUDA_TRY(cudaMalloc(&g_host.buf, bytes));
+        g_host.cap = bytes;
+    }
     *out = (char *)g_host.buf;
+    return TCAMCRF_OK;
+}
+
+static int host_event(size_t i, cudaEvent_t *ev)
+{
+    while (g_host.events.size() <= i) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g_host.events.push_back(e);
+    }
+    *ev = g_host.events[i];
     return TCAMCRF_OK;
 }
 
@@ -965,58 +1227,107 @@ static int check_device()
     return TCAMCRF_OK;
 }
 
-// Filter (and optionally loss + gradient) with host buffers.
-static int host_run(const tcamcrf_config *cfg, const float *images, const float *segs, float *as_host,
+// Filter (and optionally loss + gradient) with host buffers.  The batch is cut into groups of frames that
+// flow through three streams -- host->device copies, kernels, device->host copies -- so the PCIe transfers
+// of one group overlap the kernels of the next (truly asynchronous when the host buffers are pinned;
+// pageable buffers still work, the copies are then staged by the driver).
+static int host_run(const tcamcrf_config *cfg_in, const float *images, const float *segs, float *as_host,
                     float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out)
 {
     int rc = check_device();
     if (rc) return rc;
-    if (!images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (!cfg_in || !images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    // frames per pipeline group: ~8 groups, each still large enough to fill the GPU
+    int group = (N + 7) / 8;
+    if (group < 1) group = 1;
+    const int ngroups = (N + group - 1) / group;
+    tcamcrf_config cfg = *cfg_in;
+    if (cfg.chunk_frames <= 0 || cfg.chunk_frames > group) cfg.chunk_frames = group;
     Plan pl;
-    rc = make_plan(cfg, N, K, H, W, pl);
+    rc = make_plan(&cfg, group, K, H, W, pl);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(g_host.mu);
     const size_t P = (size_t)H * W;
-    const size_t img_bytes = align_up((size_t)N * cfg->image_stride_planes * P * sizeof(float), 256);
-    const size_t seg_bytes = align_up((size_t)N * K * P * sizeof(float), 256);
+    const size_t img_frame = (size_t)cfg.image_stride_planes * P;   // floats per image
+    const size_t seg_frame = (size_t)K * P;
+    const size_t img_bytes = align_up((size_t)N * img_frame * sizeof(float), 256);
+    const size_t seg_bytes = align_up((size_t)N * seg_frame * sizeof(float), 256);
+    const size_t scal_bytes = align_up((size_t)(2 * ngroups + 2) * sizeof(float), 256);
     char *base = nullptr;
-    rc = host_reserve(img_bytes + 3 * seg_bytes + 512 + pl.total, &base);
+    rc = host_reserve(img_bytes + 3 * seg_bytes + scal_bytes + pl.total, &base);
     if (rc) return rc;
     float *d_img = (float *)base;
     float *d_seg = (float *)(base + img_bytes);
     float *d_as = (float *)(base + img_bytes + seg_bytes);
     float *d_grad = (float *)(base + img_bytes + 2 * seg_bytes);
-    float *d_scal = (float *)(base + img_bytes + 3 * seg_bytes);  // [0]=loss, [1]=grad_out
-    char *d_ws = base + img_bytes + 3 * seg_bytes + 512;
-    cudaStream_t st = g_host.stream;
-    // only the planes the kernels read: the last image may be shorter than the stride
-    // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
-    const size_t img_floats = ((size_t)(N - 1) * cfg->image_stride_planes + cfg->channels) * P;
-    CUDA_TRY(cudaMemcpyAsync(d_img, images, img_floats * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_seg, segs, (size_t)N * K * P * sizeof(float), cudaMemcpyHostToDevice, st));
-    rc = run_filter(cfg, false, d_img, d_seg, d_as, loss_host ? d_scal : nullptr, N, K, H, W, (float)N, d_ws,
-                    pl.total, st);
-    if (rc) return rc;
-    if (as_host) CUDA_TRY(cudaMemcpyAsync(as_host, d_as, (size_t)N * K * P * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (grad_host) {
-        CUDA_TRY(cudaMemcpyAsync(d_scal + 1, &grad_out, sizeof(float), cudaMemcpyHostToDevice, st));
-        const size_t count = (size_t)N * K * P;
-        {
+    float *d_scal = (float *)(base + img_bytes + 3 * seg_bytes);  // [0]=grad_out, [1..]=loss per group, then status
+    float *d_loss = d_scal + 1;
+    int *d_status = (int *)(d_scal + 1 + ngroups);
+    char *d_ws = base + img_bytes + 3 * seg_bytes + scal_bytes;
+    cudaStream_t st = g_host.stream, s_in = g_host.s_in, s_out = g_host.s_out;
+
+    if (grad_host) CUDA_TRY(cudaMemcpyAsync(d_scal, &grad_out, sizeof(float), cudaMemcpyHostToDevice, s_in));
+    for (int g = 0; g < ngroups; g++) {
+        const int n0 = g * group;
+        const int nc = (N - n0) < group ? (N - n0) : group;
+        cudaEvent_t ev_in, ev_done;
+        rc = host_event(2 * g, &ev_in);
+        if (rc) return rc;
+        rc = host_event(2 * g + 1, &ev_done);
+        if (rc) return rc;
+        // only the planes the kernels read: the very last image may be shorter than the stride
+        // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
+        size_t img_floats = (size_t)nc * img_frame;
+        if (n0 + nc == N) img_floats = ((size_t)(nc - 1) * cfg.image_stride_planes + cfg.channels) * P;
+        CUDA_TRY(cudaMemcpyAsync(d_img + n0 * img_frame, images + n0 * img_frame, img_floats * sizeof(float),
+                                 cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame, (size_t)nc * seg_frame * sizeof(float),
+                                 cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(cudaEventRecord(ev_in, s_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+        rc = run_filter(&cfg, false, d_img + n0 * img_frame, d_seg + n0 * seg_frame, d_as + n0 * seg_frame,
+                        loss_host ? d_loss + g : nullptr, nc, K, H, W, (float)N, d_ws, pl.total, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_status + g, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (grad_host) {
             StageScope scope(kStBackward, 1, st);
-            loss_backward_kernel<<<sm_count() * 8, kThreads, 0, st>>>(d_as, d_scal + 1, d_grad, count, (float)N);
+            const size_t count = (size_t)nc * seg_frame;
+            size_t blocks = (count / 4 + kThreads - 1) / kThreads;
+            if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+            if (blocks < 1) blocks = 1;
+            loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
+                                                                        d_grad + n0 * seg_frame, count, (float)N);
         }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(grad_host, d_grad, count * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(ev_done, st));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
+        if (as_host)
+            CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
+                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        if (grad_host)
+            CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
+                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
     }
-    if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, d_scal, sizeof(float), cudaMemcpyDeviceToHost, st));
-    int status = 0;
-    CUDA_TRY(cudaMemcpyAsync(&status, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<float> losses(ngroups, 0.f);
+    std::vector<int> status(ngroups, 0);
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (status)
-        return fail(TCAMCRF_ERR_DEVICE_STATUS, "device status 0x%x (%s%s%s)", status,
-                    (status & TCAMCRF_DEV_TABLE_FULL) ? "hash table full " : "",
-                    (status & TCAMCRF_DEV_POOL_FULL) ? "vertex pool full " : "",
-                    (status & TCAMCRF_DEV_KEY_RANGE) ? "lattice coordinate out of key range" : "");
+    if (loss_host)
+        CUDA_TRY(cudaMemcpyAsync(losses.data(), d_loss, ngroups * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, ngroups * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(s_out));
+    int st_bits = 0;
+    double total = 0.0;
+    for (int g = 0; g < ngroups; g++) {
+        st_bits |= status[g];
+        total += (double)losses[g];   // every group is already divided by the full batch size N
+    }
+    if (loss_host) *loss_host = (float)total;
+    if (st_bits)
+        return fail(TCAMCRF_ERR_DEVICE_STATUS, "device status 0x%x (%s%s%s)", st_bits,
+                    (st_bits & TCAMCRF_DEV_TABLE_FULL) ? "hash table full " : "",
+                    (st_bits & TCAMCRF_DEV_POOL_FULL) ? "vertex pool full " : "",
+                    (st_bits & TCAMCRF_DEV_KEY_RANGE) ? "lattice coordinate out of key range" : "");
     return TCAMCRF_OK;
 }
 
@@ -1104,8 +1415,8 @@ int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float 
 {
     if (!as_dev || !grad_out_dev || !grad_seg_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     if (count == 0) return TCAMCRF_OK;
-    if (((uintptr_t)as_dev & 15) || ((uintptr_t)grad_seg_dev & 15))
-        return fail(TCAMCRF_ERR_INVALID, "buffers must be 16-byte aligned");
+    if (((uintptr_t)as_dev & 3) || ((uintptr_t)grad_seg_dev & 3))
+        return fail(TCAMCRF_ERR_INVALID, "buffers must be 4-byte aligned");
     size_t blocks = (count / 4 + kThreads - 1) / kThreads;
     const size_t cap = (size_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -1120,7 +1431,7 @@ int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float 
 int tcamcrf_workspace_status(void *workspace, void *cuda_stream, int *dev_status, int *vertices)
 {
     if (!workspace || !dev_status) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
-    int host[kCtrlInts];
+    int host[kCtrlResetInts];
     CUDA_TRY(cudaMemcpyAsync(host, workspace, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
     *dev_status = host[kCtrlStatus];
@@ -1157,7 +1468,7 @@ int tcamcrf_debug_lattice(const tcamcrf_config *cfg, const float *image_host, in
     if (rc) return rc;
     std::vector<int> off((size_t)dp1 * P);
     std::vector<float> bar((size_t)dp1 * P);
-    int ctrl[kCtrlInts];
+    int ctrl[kCtrlResetInts];
     CUDA_TRY(cudaMemcpyAsync(off.data(), d_ws + pl.off_offset, off.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(bar.data(), d_ws + pl.off_bary, bar.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ctrl, d_ws + pl.off_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost, st));

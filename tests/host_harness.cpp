@@ -23,10 +23,13 @@ static int embed_all(const float *feat, int n, const float *scale, int16_t *coor
         int z[D + 1], rank[D + 1];
         float b[D + 1];
         if (!embed_point<D>(f, ec, z, rank, b)) bad++;
+        unsigned long long keys[D + 1];
+        KeyCodec<D>::pack_simplex(z, rank, keys);   // the routine build_kernel uses
         for (int r = 0; r <= D; r++) {
             int q[D];
             for (int i = 0; i < D; i++) q[i] = z[i] - ((rank[i] + r > D) ? 1 : 0);
-            const unsigned long long key = KeyCodec<D>::pack(q, r);
+            const unsigned long long key = keys[r];
+            if (key != KeyCodec<D>::pack(q, r)) bad += 1000000;   // incremental packing must equal field packing
             packed[(size_t)p * (D + 1) + r] = key;
             for (int i = 0; i < D; i++)
                 coords[((size_t)p * (D + 1) + r) * D + i] = (int16_t)KeyCodec<D>::coord(key, i);

@@ -299,9 +299,10 @@ def test_device_status_poisons_outputs(torch_cuda):
     assert st & _lib.DEV_KEY_RANGE and torch.isnan(loss).all()
 
 
-@pytest.mark.parametrize("load", [0.25, 0.5, 0.9])
+@pytest.mark.parametrize("load", [0.25, 0.5, 0.9, 4.0, 64.0])
 def test_hash_load_factor_sweep(torch_cuda, oracle_mod, load):
-    """BASELINE config 4 (occupancy sweep): results do not depend on the table size."""
+    """BASELINE config 4 (occupancy sweep): results do not depend on the table size.  Loads above ~1 make the
+    primary tier smaller than the lattice, so most vertices live in the overflow tier."""
     torch = torch_cuda
     from tcam_wsol_video_b200 import ops
     n, k, h, w = 1, 2, 96, 96
@@ -311,6 +312,25 @@ def test_hash_load_factor_sweep(torch_cuda, oracle_mod, load):
     cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, hash_load=load)
     as_t, _, _ = ops.crf_forward(torch.from_numpy(img), torch.from_numpy(seg).cuda(), cfg, check=True)
     _assert_close(as_t.cpu().numpy(), want, f"load {load}")
+
+
+def test_overflow_tier_is_cleared_between_calls(torch_cuda, oracle_mod):
+    """A call that spills into the overflow tier leaves keys there; the next call on the same workspace (same
+    plan) must not see them.  Three different images back to back through a deliberately tiny primary tier."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 2, 2, 64, 80
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, hash_load=64.0)
+    for seed in (101, 102, 103):
+        img = synth.make_images(n, h, w, "noise", seed=seed)
+        seg = synth.make_segs(n, k, h, w, seed=seed)
+        want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0).reshape(seg.shape)
+        as_t, _, ws = ops.crf_forward(torch.from_numpy(img), torch.from_numpy(seg).cuda(), cfg, check=True)
+        _assert_close(as_t.cpu().numpy(), want, f"seed {seed}")
+        # vertex count equals the oracle's (stale keys would inflate it)
+        _, m_total = ops.workspace_status(ws)
+        m_want = sum(oracle_mod.port_lattice_bilateral(img[i], h, w, 15.0, 100.0).m for i in range(n))
+        assert m_total == m_want
 
 
 def test_full_size_properties_config2(torch_cuda):
