@@ -134,6 +134,9 @@ constexpr int kThreads = 256;
 #ifndef TCAMCRF_NBR_U
 #define TCAMCRF_NBR_U 1
 #endif
+#ifndef TCAMCRF_NBR_BOTH
+#define TCAMCRF_NBR_BOTH 0
+#endif
 #ifndef TCAMCRF_BLUR_U
 #define TCAMCRF_BLUR_U 1
 #endif
@@ -143,6 +146,8 @@ constexpr int kThreads = 256;
 constexpr int kCtrlStatus = 0;      // TCAMCRF_DEV_* bits
 constexpr int kCtrlLastCount = 1;   // vertices of the last chunk (sum over frames)
 constexpr int kCtrlDirtyNew = 2;    // the build of the current chunk spilled into the overflow tier
+constexpr int kCtrlTicket = 3;      // blocks of the slice kernel that have published their partial sum
+constexpr int kCtrlAccInts = 8;      // a double: running sum of seg . AS over the chunks of the call
 constexpr int kCtrlResetInts = 16;
 constexpr int kCtrlMagic = 16;      // signature of the plan that last initialised the tables
 constexpr int kCtrlDirty = 17;      // overflow tier holds keys (must be cleared before reuse)
@@ -232,7 +237,7 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
         return at;
     };
     pl.off_ctrl = take((size_t)(kCtrlCounts + pl.chunk) * sizeof(int));
-    pl.off_acc = take(4 * sizeof(double));
+    pl.off_acc = pl.off_ctrl + kCtrlAccInts * sizeof(int);   // inside the per-call reset region
     pl.off_partial = take((size_t)pl.chunk * pl.blocks_per_frame * sizeof(float));
     pl.off_table = take((size_t)pl.chunk * pl.slots * sizeof(Entry));
     pl.off_offset = take((size_t)pl.chunk * (D + 1) * pl.P * sizeof(int));
@@ -559,6 +564,9 @@ __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParam
             p.values[v * p.Kp + (i - (long long)t * p.Kp)] = 0.f;
         }
     }
+#if TCAMCRF_NBR_BOTH
+    return;
+#endif
     const int2 none = make_int2(-1, -1);
     for (long long i = tid; i < (long long)total * dp1; i += stride) {
         const int j = (int)(i / total);
@@ -610,6 +618,31 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
                 key[u] = __ldg(p.vkey + id[u]);
             }
         }
+#if TCAMCRF_NBR_BOTH
+        // variant: look both neighbours up, one coalesced int2 store, no scattered stores, no link preset
+        unsigned long long k2[kU];
+        unsigned int h2[kU];
+        uint4 e2[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            Codec::neighbour_keys(key[u], axis[u] < 0 ? 0 : axis[u], k1[u], k2[u]);
+            h[u] = (unsigned int)hash_key(k1[u]) & mask1;
+            h2[u] = (unsigned int)hash_key(k2[u]) & mask1;
+            e[u] = e2[u] = make_uint4(0, 0, 0, 0);
+            if (axis[u] >= 0) {
+                e[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h[u]));
+                e2[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h2[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            if (axis[u] < 0) continue;
+            int2 out;
+            out.x = table_lookup_from(tab[u], p.geom, k1[u], h[u], 0, e[u]);
+            out.y = table_lookup_from(tab[u], p.geom, k2[u], h2[u], 0, e2[u]);
+            p.nbr[(size_t)axis[u] * p.pool + id[u]] = out;
+        }
+#else
 #pragma unroll
         for (int u = 0; u < kU; u++) {
             unsigned long long k2;
@@ -628,6 +661,7 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
                 row[nb].y = id[u];
             }
         }
+#endif
     }
     if (tid == 0) {
         p.ctrl[kCtrlLastCount] = total;
@@ -685,8 +719,11 @@ struct PixelParams {
     const float *bary;      // [n][r][P]
     const Entry *table;
     float *values;          // [pool][Kp]
-    float *partial;         // [n][blocks_per_frame]
-    const int *ctrl;
+    float *partial;         // [n][blocks_per_frame]; null when no loss is wanted
+    int *ctrl;
+    double *acc;            // running sum of seg . AS over the chunks of this call
+    float *loss_out;        // non-null on the last chunk: receives -acc / n_norm
+    float n_norm;
     int P, K, Kp;
     long long pool;
     float alpha;
@@ -844,31 +881,36 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (threadIdx.x == 0 && p.partial) p.partial[(size_t)n * gridDim.x + blockIdx.x] = t;
     }
-}
-
-// acc[0] += sum(partial[0..count))  (one block, fixed order => deterministic)
-__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float *partial, int count, double *acc)
-{
-    __shared__ double s[32];
-    double t = 0.0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) t += (double)partial[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        t = s[threadIdx.x];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) acc[0] += t;
+    if (!p.partial) return;
+    // The last block to arrive folds the partial sums (fixed order => deterministic given AS) into the
+    // running total and, on the last chunk, writes the loss: no separate reduction launches.
+    __shared__ bool s_last;
+    __shared__ double s_sum[kThreads / 32];
+    const int nblocks = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.ctrl + kCtrlTicket, 1) == nblocks - 1;
     }
-}
-
-// loss = -(sum)/n_norm, NaN when the device status is set (dense_crf_loss.py:63-64)
-__global__ void loss_finish_kernel(const double *acc, const int *ctrl, float n_norm, float *loss)
-{
-    const float s = (float)acc[0];
-    loss[0] = ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(-s, n_norm);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += kThreads) sum += (double)__ldcg(p.partial + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = p.acc[0];
+        for (int w = 0; w < kThreads / 32; w++) total += s_sum[w];
+        p.acc[0] = total;
+        p.ctrl[kCtrlTicket] = 0;
+        if (p.loss_out) {
+            // loss = -(sum)/n_norm, NaN when the device status is set (dense_crf_loss.py:63-64)
+            const float s = (float)total;
+            p.loss_out[0] = p.ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(-s, p.n_norm);
+        }
+    }
 }
 
 // grad = ((-2*g) * AS) / n  with the reference's rounding order (dense_crf_loss.py:73)
@@ -1002,7 +1044,8 @@ static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 
 template <int D>
 static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
-                       float *as_out, int nc, char *ws, bool want_loss, cudaStream_t st)
+                       float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
+                       cudaStream_t st)
 {
     int *ctrl = (int *)(ws + pl.off_ctrl);
     Entry *table = (Entry *)(ws + pl.off_table);
@@ -1076,6 +1119,9 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
     pp.values = val0;
     pp.partial = want_loss ? partial : nullptr;
     pp.ctrl = ctrl;
+    pp.acc = acc;
+    pp.loss_out = loss_final;
+    pp.n_norm = n_norm;
     pp.P = pl.P;
     pp.K = pl.K;
     pp.Kp = pl.Kp;
@@ -1109,24 +1155,21 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
         StageScope scope(kStSlice, 1, st);
         launch_pixel<D>(false, V, pp, pgrid, st);
     }
-    if (want_loss) {
-        StageScope scope(kStLoss, 1, st);
-        loss_reduce_kernel<<<1, 1024, 0, st>>>(partial, nc * pl.blocks_per_frame, acc);
-    }
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;
 }
 
 static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
-                     float *as_out, int nc, char *ws, bool want_loss, cudaStream_t st)
+                     float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
+                     cudaStream_t st)
 {
     switch (pl.D) {
-    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
-    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
-    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
-    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
-    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
-    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, st);
+    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
     }
     return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", pl.D);
 }
@@ -1147,20 +1190,14 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
     char *ws = (char *)workspace;
     // status word + loss accumulator start clean for this call (MAGIC / DIRTY persist with the workspace)
     CUDA_TRY(cudaMemsetAsync(ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(ws + pl.off_acc, 0, 4 * sizeof(double), st));
     const size_t img_elem = u8 ? 1 : 4;
     for (int n0 = 0; n0 < N; n0 += pl.chunk) {
         const int nc = (N - n0) < pl.chunk ? (N - n0) : pl.chunk;
         const char *img = (const char *)images + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem;
+        const bool last = n0 + nc >= N;
         rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,
-                       loss != nullptr, st);
+                       loss != nullptr, last ? loss : nullptr, n_norm, st);
         if (rc) return rc;
-    }
-    if (loss) {
-        StageScope scope(kStLoss, 1, st);
-        loss_finish_kernel<<<1, 1, 0, st>>>((const double *)(ws + pl.off_acc), (const int *)(ws + pl.off_ctrl),
-                                            n_norm, loss);
-        CUDA_TRY(cudaGetLastError());
     }
     return TCAMCRF_OK;
 }
