@@ -66,6 +66,7 @@ def stage_bytes(P: int, d: int, K: int, M: float):
         "loss": 0,
         "backward": 4 * K * P,                     # gradient out
         "prepare": 0,                              # table clear: not algorithmic traffic
+        "seed": 0,
     }
 
 

@@ -137,8 +137,8 @@ int tcamcrf_loss_fwd_bwd_host(const tcamcrf_config *cfg, const float *images_hos
 /* ---- measurement hooks (bench.py) ----
  * Stage timing brackets every pipeline stage with CUDA events on the caller's stream (not capture-safe while
  * enabled).  Stages: 0 build, 1 neighbour, 2 splat, 3 blur (d+1 launches), 4 slice, 5 loss reduce/finish, 6 backward,
- * 7 prepare (table clear). */
-#define TCAMCRF_STAGES 8
+ * 7 prepare (table clear), 8 temporal max / seeding. */
+#define TCAMCRF_STAGES 9
 void tcamcrf_profile_enable(int on);
 /* Waits for the recorded events; fills accumulated milliseconds and kernel launches per stage. */
 int tcamcrf_profile_read(double *ms, long long *launches, int reset);
@@ -149,6 +149,24 @@ long long tcamcrf_launch_count(void);
 
 /* out[b] = max_t cams[b,t] with torch.maximum's NaN propagation; cams_dev [B,T,HW], out_dev [B,HW]. */
 int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream);
+
+/* Temporal max fused with seed selection, for a whole batch in one launch (one thread block per sample and
+ * per fg/bg).  Replaces, per sample, _SFG.forward / _SBG.forward (dlib/cams/tcam_seeding.py:498-592):
+ *   value = max_t cams[b,t] (* roi) + 1e-8;  candidates = the n_cand largest (fg) / smallest (bg) values,
+ *   ties broken by pixel index like torch's stable sort;  selected = top-k of p / q over the candidates in
+ *   row-major order, p = value (weighted fg) or 1, q = the caller's Exp(1) draws (torch.multinomial without
+ *   replacement is exactly this), so the result is bit-exact given the same draws.
+ * cams_dev [B,T,HW]; roi_dev [B,HW] int64 or NULL (fg only); q_dev: draws of all (sample, fg|bg) pairs,
+ * q_offset_dev [B,2] their starts; n_cand_dev [B,2] (0 = emit no seed); k_fg/k_bg seeds per sample.
+ * Outputs: cam_max_dev [B,HW]; sel_dev [B,2,kmax] pixel indices (-1 = unused); scratch_dev [B,2,HW] floats. */
+int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const float *q_dev,
+                     const int *q_offset_dev, const int *n_cand_dev, int k_fg, int k_bg, int weighted_fg, int B, int HW,
+                     float *cam_max_dev, float *scratch_dev, int *sel_dev, int kmax, void *cuda_stream);
+
+/* Label map from the selected seeds: flat ksz x ksz dilation of fg and bg seeds, pixels claimed by both ->
+ * ignore; out_dev [B,H,W] int64 in {ignore_idx, 0, 1} (dlib/cams/tcam_seeding.py:212-254). */
+int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
+                     int64_t *out_dev, void *cuda_stream);
 
 #ifdef __cplusplus
 }

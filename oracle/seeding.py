@@ -1,0 +1,122 @@
+"""oracle/seeding.py -- TEST INFRASTRUCTURE ONLY.
+
+Plain-torch restatement of the reference's temporal-CAM max and seed selection, line by line, so that the
+CUDA kernels (tcam_seed_select / tcam_seed_labels) can be compared with it bit for bit on the same random
+stream.  It runs on whatever device its inputs are on and uses the very same torch calls as the reference
+(``torch.sort(stable=True)``, ``nonzero``, ``Tensor.multinomial``), in the same order:
+
+  temporal_max         <- dlib/datasets/wsol_loader.py:591-600   (chain of torch.maximum)
+  sample_fg            <- _SFG.forward      dlib/cams/tcam_seeding.py:498-544
+  sample_bg            <- _SBG.forward      dlib/cams/tcam_seeding.py:555-592
+  one_sample           <- _OneSample.forward  tcam_seeding.py:453-487   (roi given or unused)
+  flat_dilation        <- kornia==0.6.4 kornia.morphology.dilation with a ones kernel (third-party, not in
+                          /root/reference; requirements.txt:36): out = max over the ksz x ksz window whose
+                          origin is (ksz//2, ksz//2), positions outside the image ignored (geodesic border)
+  tcam_seeder_forward  <- TCAMSeeder.forward  tcam_seeding.py:178-256
+
+Parity of flat_dilation and of torch 2.11's multinomial/sort against the versions the reference pins
+(torch 1.11, kornia 0.6.4) is UNPINNED: no reference test fixes them and those packages are not installed
+here.  Their documented semantics are restated.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+SEED_UNIFORM = 'seed_uniform'
+SEED_WEIGHTED = 'seed_weighted'
+
+
+def temporal_max(cams: torch.Tensor) -> torch.Tensor:
+    """cams [B,T,...] -> [B,...]: std_cam = maximum(std_cam, cam_t) frame after frame."""
+    out = cams[:, 0]
+    for t in range(1, cams.shape[1]):
+        out = torch.maximum(out, cams[:, t])
+    return out
+
+
+def sample_fg(cam, roi, fg, max_p, max_, seed_tech):
+    h, w = cam.shape
+    if roi is not None:
+        n = roi.sum()
+        _cam = cam * roi
+        _cam = _cam + 1e-8
+    else:
+        n = h * w
+        _cam = cam + 1e-8
+    n = int(max_p * n)
+    _cam_flatten = _cam.view(h * w)
+    val, idx_ = torch.sort(_cam_flatten, dim=0, descending=True, stable=True)
+    if (n > 0) and (max_ > 0):
+        tmp = _cam_flatten * 0.
+        tmp[idx_[:n]] = 1
+        tmp = tmp.view(h, w)
+        _idx = torch.nonzero(tmp, as_tuple=True)
+        if seed_tech == SEED_UNIFORM:
+            probs = torch.ones(n, dtype=torch.float, device=cam.device)
+        elif seed_tech == SEED_WEIGHTED:
+            probs = _cam[_idx[0], _idx[1]]
+            assert probs.numel() == n
+        else:
+            raise NotImplementedError(seed_tech)
+        selected = probs.multinomial(num_samples=min(max_, n), replacement=False)
+        fg[_idx[0][selected], _idx[1][selected]] = 1
+    return fg
+
+
+def sample_bg(cam, bg, min_p, min_):
+    h, w = cam.shape
+    n = int(min_p * h * w)
+    _cam = cam + 1e-8
+    _cam_flatten = _cam.view(h * w)
+    val, idx_ = torch.sort(_cam_flatten, dim=0, descending=False, stable=True)
+    if (n > 0) and (min_ > 0):
+        tmp = _cam_flatten * 0.
+        tmp[idx_[:n]] = 1
+        tmp = tmp.view(h, w)
+        _idx = torch.nonzero(tmp, as_tuple=True)
+        probs = torch.ones(n, dtype=torch.float, device=cam.device)   # _SBG is always built with SEED_UNIFORM
+        selected = probs.multinomial(num_samples=min(min_, n), replacement=False)
+        bg[_idx[0][selected], _idx[1][selected]] = 1
+    return bg
+
+
+def one_sample(cam, roi, *, min_p, max_p, min_, max_, seed_tech, use_roi):
+    h, w = cam.shape
+    fg = torch.zeros((h, w), dtype=torch.long, device=cam.device)
+    bg = torch.zeros((h, w), dtype=torch.long, device=cam.device)
+    if cam.min() == cam.max():
+        return fg, bg
+    _roi = roi if use_roi else None
+    fg = sample_fg(cam, _roi, fg, max_p, max_, seed_tech)
+    bg = sample_bg(cam, bg, min_p, min_)
+    return fg, bg
+
+
+def flat_dilation(x: torch.Tensor, ksz: int) -> torch.Tensor:
+    """x [B,1,H,W] (0/1) -> same shape: flat ksz x ksz dilation, window origin ksz//2, outside ignored."""
+    if ksz == 1:
+        return x
+    o = ksz // 2
+    padded = F.pad(x.float(), (o, ksz - o - 1, o, ksz - o - 1), value=float('-inf'))
+    return F.max_pool2d(padded, kernel_size=ksz, stride=1).to(x.dtype)
+
+
+def tcam_seeder_forward(x, roi=None, *, seed_tech, min_, max_, min_p, max_p, ksz, ignore_idx, use_roi):
+    b, d, h, w = x.shape
+    assert d == 1
+    out = torch.zeros((b, h, w), dtype=torch.long, device=x.device) + ignore_idx
+    all_fg = torch.zeros((b, h, w), dtype=torch.long, device=x.device)
+    all_bg = torch.zeros((b, h, w), dtype=torch.long, device=x.device)
+    for i in range(b):
+        _roi = roi[i].squeeze() if roi is not None else None
+        all_fg[i], all_bg[i] = one_sample(x[i].squeeze(), _roi, min_p=min_p, max_p=max_p, min_=min_, max_=max_,
+                                          seed_tech=seed_tech, use_roi=use_roi)
+    all_fg = flat_dilation(all_fg.unsqueeze(1), ksz).squeeze(1)
+    all_bg = flat_dilation(all_bg.unsqueeze(1), ksz).squeeze(1)
+    outer = all_fg + all_bg
+    all_fg[outer == 2] = 0
+    all_bg[outer == 2] = 0
+    out[all_fg == 1] = 1
+    out[all_bg == 1] = 0
+    return out.detach()

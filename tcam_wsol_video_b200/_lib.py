@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libtcamcrf.so")
 SOURCES = [os.path.join(CSRC, "tcamcrf.cu")]
-HEADERS = [os.path.join(CSRC, "lattice.cuh"), os.path.join(os.path.dirname(_HERE), "include", "tcamcrf.h")]
+HEADERS = [os.path.join(CSRC, "lattice.cuh"), os.path.join(CSRC, "seed.cuh"), os.path.join(os.path.dirname(_HERE), "include", "tcamcrf.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 FEAT_XY_RGB = 0
 FEAT_COLOR = 1
 
-STAGES = ("build", "neighbour", "splat", "blur", "slice", "loss", "backward", "prepare")
+STAGES = ("build", "neighbour", "splat", "blur", "slice", "loss", "backward", "prepare", "seed")
 
 DEV_TABLE_FULL = 1
 DEV_POOL_FULL = 2
@@ -109,6 +109,9 @@ SIGNATURES = {
     "tcamcrf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
     "tcamcrf_launch_count": (ctypes.c_longlong, []),
     "tcam_temporal_max": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcam_seed_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "tcam_seed_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
 }
 
 

@@ -1,0 +1,283 @@
+// seed.cuh -- temporal-CAM max fused with fg/bg seed selection, and the seed-label map.
+// Included by tcamcrf.cu (one translation unit, one .so).
+//
+// What it replaces in the reference:
+//   tcam_seed_select  <- the chain of torch.maximum over the frames' CAMs (dlib/datasets/wsol_loader.py:591-600)
+//                        + _SFG.forward / _SBG.forward for every sample of the batch
+//                        (dlib/cams/tcam_seeding.py:498-592): `cam*roi + 1e-8`, stable sort, top-n mask,
+//                        row-major candidates, multinomial without replacement
+//   tcam_seed_labels  <- TCAMSeeder.forward's tail (tcam_seeding.py:239-254): kornia flat ksz x ksz dilation
+//                        of the fg and bg one-hot maps, fg/bg conflict -> ignore, labels {ignore, 0, 1}
+//
+// The reference sorts all H*W values twice per sample only to find which pixels are the n largest /
+// smallest; here ONE thread block per (sample, fg|bg) finds the n-th value with a 4-pass radix select and
+// breaks ties by pixel index, which is what a stable sort does.  torch.multinomial without replacement is
+// argmax / top-k of p / q with q ~ Exp(1) drawn in candidate (row-major) order; the draws are an INPUT, so
+// the selection is bit-exact given the same draws.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tcamcrf {
+
+constexpr int kSeedThreads = 1024;
+
+// ascending-order key of a float (NaN sorts last, like torch.sort); -0.0 is folded onto +0.0
+__device__ __forceinline__ unsigned int float_order_key(float v)
+{
+    v = v + 0.0f;
+    const unsigned int b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// block-wide exclusive scan of one int per thread (kSeedThreads threads); returns the exclusive prefix and the
+// block total through `total`
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_warp may still be read from the previous scan
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;          // exclusive warp offsets
+        if (lane == 31) s_warp[32] = wi;  // block total
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+struct SeedParams {
+    const float *cams;      // [B][T][HW]
+    const long long *roi;   // [B][HW] or null
+    const float *q;         // exponential draws, all samples concatenated
+    const int *q_offset;    // [B][2] start of the (sample, fg|bg) draws in q
+    const int *n_cand;      // [B][2] candidates (0 -> no seed: degenerate cam, n == 0, or min_/max_ == 0)
+    float *cam_max;         // [B][HW] out: temporal max (before roi / epsilon)
+    float *scratch;         // [B][2][HW] scores
+    int *sel;               // [B][2][kmax] out: selected pixel indices, -1 = unused
+    int T, HW, kmax;
+    int k_fg, k_bg;
+    int weighted_fg;
+};
+
+// grid (2, B): blockIdx.x = 0 foreground, 1 background
+__global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const SeedParams p)
+{
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[33];
+    __shared__ unsigned int s_prefix;
+    __shared__ int s_need;
+    __shared__ float s_best_v[32];
+    __shared__ int s_best_i[32];
+
+    const int b = blockIdx.y;
+    const bool fg = blockIdx.x == 0;
+    const int tid = threadIdx.x;
+    const int HW = p.HW;
+    const float *cam0 = p.cams + (size_t)b * p.T * HW;
+    float *cmax = p.cam_max + (size_t)b * HW;
+    const long long *roi = (fg && p.roi) ? p.roi + (size_t)b * HW : nullptr;
+    float *score = p.scratch + ((size_t)b * 2 + (fg ? 0 : 1)) * HW;
+    int *sel = p.sel + ((size_t)b * 2 + (fg ? 0 : 1)) * p.kmax;
+    const int n = p.n_cand[b * 2 + (fg ? 0 : 1)];
+    int k = fg ? p.k_fg : p.k_bg;
+    if (k > n) k = n;
+    if (k > p.kmax) k = p.kmax;
+
+    // pass 0 (foreground block only writes it): temporal max, float4 over the T planes where HW allows
+    if (fg) {
+        if ((HW & 3) == 0) {
+            for (int i = tid; i < HW / 4; i += kSeedThreads) {
+                float4 m = __ldg(reinterpret_cast<const float4 *>(cam0) + i);
+                for (int t = 1; t < p.T; t++) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(cam0 + (size_t)t * HW) + i);
+                    // torch.maximum: NaN if either operand is NaN
+                    m.x = (m.x != m.x) ? m.x : ((v.x != v.x) ? v.x : (v.x > m.x ? v.x : m.x));
+                    m.y = (m.y != m.y) ? m.y : ((v.y != v.y) ? v.y : (v.y > m.y ? v.y : m.y));
+                    m.z = (m.z != m.z) ? m.z : ((v.z != v.z) ? v.z : (v.z > m.z ? v.z : m.z));
+                    m.w = (m.w != m.w) ? m.w : ((v.w != v.w) ? v.w : (v.w > m.w ? v.w : m.w));
+                }
+                reinterpret_cast<float4 *>(cmax)[i] = m;
+            }
+        } else {
+            for (int i = tid; i < HW; i += kSeedThreads) {
+                float m = __ldg(cam0 + i);
+                for (int t = 1; t < p.T; t++) {
+                    const float v = __ldg(cam0 + (size_t)t * HW + i);
+                    m = (m != m) ? m : ((v != v) ? v : (v > m ? v : m));
+                }
+                cmax[i] = m;
+            }
+        }
+    }
+    for (int i = tid; i < p.kmax; i += kSeedThreads) sel[i] = -1;
+    if (n <= 0 || k <= 0) return;
+
+    // value of pixel i as the reference scores it: cam*roi + 1e-8 (fg with roi) or cam + 1e-8
+    // (tcam_seeding.py:511-517,564-565).  The background block recomputes the max instead of waiting for
+    // the foreground block's cam_max.
+    auto value_at = [&](int i) -> float {
+        float m = __ldg(cam0 + i);
+        for (int t = 1; t < p.T; t++) {
+            const float v = __ldg(cam0 + (size_t)t * HW + i);
+            m = (m != m) ? m : ((v != v) ? v : (v > m ? v : m));
+        }
+        if (roi) m = __fmul_rn(m, (float)__ldg(roi + i));
+        return __fadd_rn(m, 1e-8f);
+    };
+    // selection key: the n SMALLEST keys are the candidates (descending order for the foreground)
+    auto key_at = [&](int i) -> unsigned int {
+        const unsigned int u = float_order_key(value_at(i));
+        return fg ? ~u : u;
+    };
+
+    // radix select, 8 bits at a time from the top: after 4 passes `prefix` is the n-th smallest key
+    unsigned int prefix = 0;
+    int need = n;  // rank of the wanted key among the keys that share the current prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += kSeedThreads) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned int himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < HW; i += kSeedThreads) {
+            const unsigned int key = key_at(i);
+            if ((key & himask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0, bin = 0;
+            for (; bin < 256; bin++) {
+                if (run + s_hist[bin] >= need) break;
+                run += s_hist[bin];
+            }
+            s_prefix = prefix | ((unsigned int)bin << shift);
+            s_need = need - run;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        need = s_need;
+        __syncthreads();
+    }
+    const unsigned int kth = prefix;   // keys < kth are candidates; of the keys == kth the first `need` by index
+
+    // candidates in row-major order -> their draw q[rank]; score = p / q  (torch.multinomial without replacement)
+    const float *q = p.q + p.q_offset[b * 2 + (fg ? 0 : 1)];
+    const bool weighted = fg && p.weighted_fg;
+    int ties_before = 0, cands_before = 0;
+    for (int base = 0; base < HW; base += kSeedThreads) {
+        const int i = base + tid;
+        unsigned int key = 0xffffffffu;
+        float val = 0.f;
+        if (i < HW) {
+            val = value_at(i);
+            const unsigned int u = float_order_key(val);
+            key = fg ? ~u : u;
+        }
+        const int is_tie = (i < HW && key == kth) ? 1 : 0;
+        int tie_total, cand_total;
+        const int tie_rank = ties_before + block_exclusive_scan(is_tie, s_warp, tie_total);
+        const int is_cand = (i < HW && (key < kth || (is_tie && tie_rank < need))) ? 1 : 0;
+        const int cand_rank = cands_before + block_exclusive_scan(is_cand, s_warp, cand_total);
+        if (i < HW) {
+            float sc = -INFINITY;
+            if (is_cand) sc = __fdiv_rn(weighted ? val : 1.0f, __ldg(q + cand_rank));
+            score[i] = sc;
+        }
+        ties_before += tie_total;
+        cands_before += cand_total;
+    }
+    __syncthreads();
+
+    // k rounds of block argmax (lowest index wins ties); a selected pixel is retired with -inf
+    for (int round = 0; round < k; round++) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < HW; i += kSeedThreads) {
+            const float s = score[i];
+            if (s > bv || (s == bv && i < bi && s != -INFINITY)) {
+                bv = s;
+                bi = i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if ((tid & 31) == 0) {
+            s_best_v[tid >> 5] = bv;
+            s_best_i[tid >> 5] = bi;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            bv = s_best_v[tid];
+            bi = s_best_i[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            if (tid == 0) {
+                if (bv > -INFINITY && bi < HW) {
+                    sel[round] = bi;
+                    score[bi] = -INFINITY;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// out[b][y][x] = 1 if a fg seed dilates onto the pixel, 0 if a bg seed does, ignore if none or both
+__global__ void __launch_bounds__(256) seed_labels_kernel(const int *__restrict__ sel, int kmax, int B, int H, int W,
+                                                          int ksz, long long ignore_idx, long long *__restrict__ out)
+{
+    // kornia 0.6.4 dilation with a flat ksz x ksz kernel: out[y] = max_{d in [0,ksz)} in[y + d - origin],
+    // origin = ksz / 2  =>  a seed at sy reaches y in [sy - (ksz-1-origin), sy + origin]
+    const int origin = ksz / 2;
+    const int back = ksz - 1 - origin;
+    const long long total = (long long)B * H * W;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int b = (int)(i / ((long long)H * W));
+        const int px = (int)(i - (long long)b * H * W);
+        const int y = px / W, x = px - y * W;
+        bool near[2] = {false, false};
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int *s = sel + ((size_t)b * 2 + c) * kmax;
+            for (int j = 0; j < kmax; j++) {
+                const int sp = __ldg(s + j);
+                if (sp < 0) break;
+                const int sy = sp / W, sx = sp - sy * W;
+                if (y >= sy - back && y <= sy + origin && x >= sx - back && x <= sx + origin) near[c] = true;
+            }
+        }
+        long long label = ignore_idx;
+        if (near[0] != near[1]) label = near[0] ? 1 : 0;   // claimed by both -> neither (tcam_seeding.py:247-250)
+        out[i] = label;
+    }
+}
+
+}  // namespace tcamcrf

@@ -42,6 +42,7 @@
 
 #include "../../include/tcamcrf.h"
 #include "lattice.cuh"
+#include "seed.cuh"
 
 namespace tcamcrf {
 
@@ -70,7 +71,7 @@ static int fail(int code, const char *fmt, ...)
 // ---------------------------------------------------------------------------
 // optional per-stage timing (CUDA events on the caller's stream) + launch counter
 // ---------------------------------------------------------------------------
-enum Stage { kStBuild = 0, kStNeighbour, kStSplat, kStBlur, kStSlice, kStLoss, kStBackward, kStPrepare, kStCount };
+enum Stage { kStBuild = 0, kStNeighbour, kStSplat, kStBlur, kStSlice, kStLoss, kStBackward, kStPrepare, kStSeed, kStCount };
 static_assert(kStCount == TCAMCRF_STAGES, "stage list and header disagree");
 
 struct Profiler {
@@ -1629,6 +1630,55 @@ long long tcamcrf_launch_count(void)
     return g_prof.total_launches;
 }
 
+int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const float *q_dev,
+                     const int *q_offset_dev, const int *n_cand_dev, int k_fg, int k_bg, int weighted_fg, int B, int HW,
+                     float *cam_max_dev, float *scratch_dev, int *sel_dev, int kmax, void *cuda_stream)
+{
+    if (!cams_dev || !q_dev || !q_offset_dev || !n_cand_dev || !cam_max_dev || !scratch_dev || !sel_dev)
+        return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || T < 1 || HW < 1 || kmax < 1 || k_fg < 0 || k_bg < 0)
+        return fail(TCAMCRF_ERR_INVALID, "B,T,HW,kmax must be positive and k_fg,k_bg non-negative");
+    SeedParams sp;
+    sp.cams = cams_dev;
+    sp.roi = reinterpret_cast<const long long *>(roi_dev);
+    sp.q = q_dev;
+    sp.q_offset = q_offset_dev;
+    sp.n_cand = n_cand_dev;
+    sp.cam_max = cam_max_dev;
+    sp.scratch = scratch_dev;
+    sp.sel = sel_dev;
+    sp.T = T;
+    sp.HW = HW;
+    sp.kmax = kmax;
+    sp.k_fg = k_fg;
+    sp.k_bg = k_bg;
+    sp.weighted_fg = weighted_fg;
+    {
+        StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+        seed_select_kernel<<<dim3(2, B), kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(sp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
+int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
+                     int64_t *out_dev, void *cuda_stream)
+{
+    if (!sel_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || H < 1 || W < 1 || kmax < 1 || ksz < 1) return fail(TCAMCRF_ERR_INVALID, "B,H,W,kmax,ksz must be positive");
+    const long long total = (long long)B * H * W;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    {
+        StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+        seed_labels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
+            sel_dev, kmax, B, H, W, ksz, ignore_idx, reinterpret_cast<long long *>(out_dev));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
 int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream)
 {
     if (!cams_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
@@ -1637,6 +1687,7 @@ int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int H
     long long blocks = (total + kThreads - 1) / kThreads;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
     temporal_max_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)cuda_stream>>>(cams_dev, out_dev, T, HW, total);
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;

@@ -1,0 +1,247 @@
+"""TCAMSeeder -- drop-in for ``dlib/cams/tcam_seeding.py::TCAMSeeder`` of the reference.
+
+Same constructor arguments, same ``forward(x, roi=None)`` contract (``x`` CAMs ``[B,1,H,W]`` in [0,1],
+``roi`` long ``[B,1,H,W]``; returns long ``[B,H,W]`` in {ignore, 0 bg, 1 fg}), ``set_seed_tech``,
+``use_all_roi`` and ``extra_repr``.  The reference loops over the samples in Python and, per sample, runs two
+full stable sorts, ``nonzero``, ``multinomial`` and several host syncs (tcam_seeding.py:232-237,453-592);
+here the whole batch is two kernel launches (``tcam_seed_select`` + ``tcam_seed_labels``, csrc/seed.cuh) and
+ONE host sync (to size the random draws exactly like the reference does).
+
+Random draws.  ``torch.multinomial(probs, k, replacement=False)`` is ``topk(probs / q)`` with
+``q = empty_like(probs).exponential_(1)``.  With ``rng_parity=True`` (default) the draws are taken from the
+current torch CUDA generator with the same sizes and in the same order as the reference's calls
+(sample 0 fg, sample 0 bg, sample 1 fg, ...), so for the same seed the seeds are bit-identical to the
+reference's.  ``rng_parity=False`` draws everything in one call (same distribution, different stream).
+
+Not supported (raises): ``use_roi=True`` with ``roi=None`` -- the reference then computes the ROI on the CPU
+with scikit-image's Otsu (tcam_seeding.py:476-479), which is outside this path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+__all__ = ['TCAMSeeder', 'SEED_UNIFORM', 'SEED_WEIGHTED']
+
+# dlib/configure/constants.py:352-354,368-372
+SEED_UNIFORM = 'seed_uniform'
+SEED_WEIGHTED = 'seed_weighted'
+SEED_TECHS = [SEED_UNIFORM, SEED_WEIGHTED]
+ROI_ALL = 'roi_all'
+ROI_H_DENSITY = 'roi_high_density'
+ROI_LARGEST = 'largest'
+ROI_SELECT = [ROI_ALL, ROI_H_DENSITY, ROI_LARGEST]
+
+
+class TCAMSeeder(nn.Module):
+    def __init__(self,
+                 seed_tech: str,
+                 min_: int,
+                 max_: int,
+                 max_p: float,
+                 min_p: float,
+                 fg_erode_k: int,
+                 fg_erode_iter: int,
+                 ksz: int,
+                 support_background: bool,
+                 multi_label_flag: bool,
+                 seg_ignore_idx: int,
+                 cuda_id: int,
+                 roi_method: str,
+                 p_min_area_roi: float,
+                 use_roi: bool,
+                 rng_parity: bool = True
+                 ):
+        super(TCAMSeeder, self).__init__()
+        assert seed_tech in SEED_TECHS, seed_tech
+        self.seed_tech = seed_tech
+        assert not multi_label_flag
+        assert isinstance(cuda_id, int)
+        assert cuda_id >= 0, cuda_id
+        self._device = torch.device('cuda', cuda_id)
+        assert isinstance(ksz, int)
+        assert ksz > 0
+        self.ksz = ksz
+        assert isinstance(min_, int)
+        assert isinstance(max_, int)
+        assert min_ >= 0
+        assert max_ >= 0
+        assert min_ + max_ > 0
+        self.min_ = min_
+        self.max_ = max_
+        assert isinstance(min_p, float)
+        assert 0. <= min_p <= 1.
+        self.min_p = min_p
+        assert isinstance(max_p, float)
+        assert 0. <= max_p <= 1.
+        self.max_p = max_p
+        assert isinstance(fg_erode_k, int)
+        assert fg_erode_k >= 1
+        self.fg_erode_k = fg_erode_k
+        assert isinstance(fg_erode_iter, int)
+        assert fg_erode_iter >= 0
+        self.fg_erode_iter = fg_erode_iter
+        self.support_background = support_background
+        self.multi_label_flag = multi_label_flag
+        self.ignore_idx = seg_ignore_idx
+        assert roi_method in ROI_SELECT, roi_method
+        self.roi_method = roi_method
+        assert 0. < p_min_area_roi < 1., p_min_area_roi
+        self.p_min_area_roi = p_min_area_roi
+        self.use_roi = use_roi
+        self.rng_parity = rng_parity
+
+    def set_seed_tech(self, seed_tech):
+        assert seed_tech in SEED_TECHS, seed_tech
+        self.seed_tech = seed_tech
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _erode(self, roi: torch.Tensor) -> torch.Tensor:
+        """fg_erode_iter flat erosions of a binary map [B,1,H,W] (kornia.morphology.erosion with a ones
+        kernel and the geodesic border = min over the part of the window that lies inside the image)."""
+        if self.fg_erode_iter == 0:
+            return roi
+        assert self.fg_erode_k > 1
+        k = self.fg_erode_k
+        o = k // 2
+        out = roi.float()
+        for _ in range(self.fg_erode_iter):
+            padded = F.pad(-out, (o, k - o - 1, o, k - o - 1), value=float('-inf'))
+            out = -F.max_pool2d(padded, kernel_size=k, stride=1)
+        return out.to(roi.dtype)
+
+    def _candidate_counts(self, x: torch.Tensor, roi: Optional[torch.Tensor]) -> Tuple[np.ndarray, np.ndarray]:
+        """Per-sample numbers of fg / bg candidates, computed like the reference (one host sync)."""
+        b, _, h, w = x.shape
+        flat = x.reshape(b, -1)
+        degenerate = (flat.amin(dim=1) == flat.amax(dim=1)).long()       # tcam_seeding.py:465
+        if roi is not None:
+            stats = torch.stack([degenerate, roi.reshape(b, -1).sum(dim=1).long()], dim=1).cpu().numpy()
+        else:
+            stats = torch.stack([degenerate, torch.zeros_like(degenerate)], dim=1).cpu().numpy()
+        n_bg = int(self.min_p * h * w)                                    # tcam_seeding.py:567
+        counts = np.zeros((b, 2), dtype=np.int32)
+        for i in range(b):
+            if stats[i, 0]:
+                continue                                                   # flat CAM: no seeds at all
+            if roi is not None:
+                # int(max_p * roi.sum()): a python float times a 0-dim long tensor is a float32 product
+                n_fg = int(np.float32(self.max_p) * np.float32(stats[i, 1]))   # tcam_seeding.py:510,519
+            else:
+                n_fg = int(self.max_p * (h * w))                          # tcam_seeding.py:515,519
+            counts[i, 0] = n_fg if self.max_ > 0 else 0
+            counts[i, 1] = n_bg if self.min_ > 0 else 0
+        return counts, stats
+
+    def _draws(self, counts: np.ndarray, device: torch.device) -> Tuple[torch.Tensor, np.ndarray]:
+        offsets = np.zeros_like(counts)
+        total = 0
+        for i in range(counts.shape[0]):
+            for c in range(2):
+                offsets[i, c] = total
+                total += int(counts[i, c])
+        q = torch.empty(max(total, 1), dtype=torch.float32, device=device)
+        if total == 0:
+            return q, offsets
+        if self.rng_parity:
+            # same sizes, same order as the reference's multinomial calls (fg then bg, sample by sample)
+            for i in range(counts.shape[0]):
+                for c in range(2):
+                    n = int(counts[i, c])
+                    if n > 0:
+                        q[offsets[i, c]:offsets[i, c] + n].exponential_(1)
+        else:
+            q.exponential_(1)
+        return q, offsets
+
+    def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts: np.ndarray):
+        """cams [B,T,H,W] float32 CUDA -> (labels [B,H,W] long, cam_max [B,H,W])."""
+        lib = _lib.load()
+        b, t, h, w = cams.shape
+        device = cams.device
+        q, offsets = self._draws(counts, device)
+        kmax = max(self.max_, self.min_, 1)
+        meta = torch.from_numpy(np.concatenate([offsets.reshape(-1), counts.reshape(-1)]).astype(np.int32)).to(device)
+        q_off, n_cand = meta[: 2 * b], meta[2 * b:]
+        cam_max = torch.empty((b, h, w), dtype=torch.float32, device=device)
+        scratch = torch.empty((b, 2, h * w), dtype=torch.float32, device=device)
+        sel = torch.empty((b, 2, kmax), dtype=torch.int32, device=device)
+        out = torch.empty((b, h, w), dtype=torch.long, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(lib.tcam_seed_select(cams.data_ptr(), t, roi.data_ptr() if roi is not None else None,
+                                            q.data_ptr(), q_off.data_ptr(), n_cand.data_ptr(), self.max_, self.min_,
+                                            1 if self.seed_tech == SEED_WEIGHTED else 0, b, h * w,
+                                            cam_max.data_ptr(), scratch.data_ptr(), sel.data_ptr(), kmax, stream),
+                       'tcam_seed_select')
+            _lib.check(lib.tcam_seed_labels(sel.data_ptr(), kmax, b, h, w, self.ksz, int(self.ignore_idx),
+                                            out.data_ptr(), stream), 'tcam_seed_labels')
+        return out, cam_max
+
+    def _prep(self, x: torch.Tensor, roi: Optional[torch.Tensor]):
+        assert isinstance(x, torch.Tensor)
+        assert x.ndim == 4
+        if not x.is_cuda:
+            raise _lib.TcamCrfError('TCAMSeeder needs CUDA tensors: this package has no CPU path')
+        if roi is not None:
+            assert torch.is_tensor(roi)
+            assert roi.ndim == 4  # b, 1, h, w
+            assert roi.shape[0] == x.shape[0], f'{roi.shape[0]}, {x.shape[0]}'
+            assert roi.shape[1] == 1, roi.shape[1]
+            assert roi.shape[2:] == x.shape[2:]
+        if self.ksz < 1:
+            raise ValueError
+        _roi = None
+        if self.use_roi:
+            if roi is None:
+                raise NotImplementedError('use_roi=True needs the roi tensor (the reference falls back to a CPU '
+                                          'scikit-image Otsu, which is outside this path)')
+            _roi = self._erode(roi.to(x.device)).long().contiguous()
+        return x.detach().float().contiguous(), _roi
+
+    # -- reference API -----------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, roi: torch.Tensor = None) -> torch.Tensor:
+        x, _roi = self._prep(x, roi)
+        b, d, h, w = x.shape
+        assert d == 1, d  # todo multilabel.
+        counts, _ = self._candidate_counts(x, _roi)
+        out, _ = self._select(x, _roi, counts)
+        return out.detach()
+
+    def forward_stack(self, cams: torch.Tensor, roi: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fused temporal max + seeding: cams [B,T,H,W] (current frame and its neighbours' CAMs at the same
+        resolution).  Returns (seeds [B,H,W] long, cam_max [B,H,W]); identical to
+        ``forward(cams.max-chain over T)`` (dlib/datasets/wsol_loader.py:591-600 followed by TCAMSeeder)."""
+        assert cams.ndim == 4
+        x_max = ops.temporal_cam_max(cams.detach().float().contiguous()).unsqueeze(1)   # for the counts only
+        x_max, _roi = self._prep(x_max, roi)
+        counts, _ = self._candidate_counts(x_max, _roi)
+        out, cam_max = self._select(cams.detach().float().contiguous(), _roi, counts)
+        return out.detach(), cam_max
+
+    def use_all_roi(self, x: torch.Tensor, roi: torch.Tensor = None) -> torch.Tensor:
+        """Every roi pixel becomes foreground, everything else ignore (tcam_seeding.py:258-299)."""
+        assert isinstance(x, torch.Tensor)
+        assert x.ndim == 4
+        assert roi is not None
+        assert roi.ndim == 4
+        assert roi.shape[0] == x.shape[0] and roi.shape[1] == 1 and roi.shape[2:] == x.shape[2:]
+        b, d, h, w = x.shape
+        assert d == 1, d
+        out = torch.zeros((b, h, w), dtype=torch.long, requires_grad=False, device=x.device) + self.ignore_idx
+        out[roi.squeeze(1) == 1] = 1
+        return out.detach()
+
+    def extra_repr(self):
+        return f'min_={self.min_}, max_={self.max_}, min_p={self.min_p},' \
+               f'max_p={self.max_p}, ksz={self.ksz}, fg_erode_k: ' \
+               f'{self.fg_erode_k}, fg_erode_iter: {self.fg_erode_iter}' \
+               f'support_background={self.support_background},' \
+               f'multi_label_flag={self.multi_label_flag}, ' \
+               f'seg_ignore_idx={self.ignore_idx}, seed_tech={self.seed_tech}'

@@ -1,0 +1,129 @@
+"""GPU suite (-m gpu): temporal-CAM max and fg/bg seeding, bit-exact against the torch restatement of the
+reference (oracle/seeding.py) when both consume the same random stream."""
+import numpy as np
+import pytest
+
+from tcam_wsol_video_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _make(torch, b, h, w, seed, low_res=28):
+    """CAMs like the trainer sees them: low-res maps upsampled bilinearly to the image size
+    (train_wsol.py:417-432), plus an Otsu-like roi."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand((b, 1, low_res, low_res), generator=g)
+    cam = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)
+    roi = (cam >= cam.flatten(1).median(dim=1).values.view(b, 1, 1, 1)).long()
+    return cam.cuda(), roi.cuda()
+
+
+def _seeder(**kw):
+    from tcam_wsol_video_b200.tcam_seeding import TCAMSeeder
+    base = dict(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11, fg_erode_iter=0,
+                ksz=3, support_background=True, multi_label_flag=False, seg_ignore_idx=-255, cuda_id=0,
+                roi_method="roi_all", p_min_area_roi=0.05, use_roi=True)
+    base.update(kw)
+    return TCAMSeeder(**base)
+
+
+CONFIGS = [
+    dict(),                                                       # README recipe
+    dict(seed_tech="seed_uniform"),
+    dict(min_=10, max_=10, ksz=1, min_p=0.2, max_p=0.2, use_roi=False),   # config.py defaults
+    dict(min_=3, max_=5, ksz=5),
+    dict(min_=0, max_=2, ksz=4),
+    dict(min_=2, max_=0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[str(i) for i in range(len(CONFIGS))])
+@pytest.mark.parametrize("shape", [(4, 224, 224), (3, 37, 53)])
+def test_seeds_bit_exact_vs_reference_restatement(torch_cuda, cfg, shape):
+    torch = torch_cuda
+    from oracle import seeding as ref
+    b, h, w = shape
+    cam, roi = _make(torch, b, h, w, seed=5)
+    cam[1] = 0.25                      # a flat CAM: the reference emits no seed for it and draws nothing
+    mod = _seeder(**cfg)
+    torch.manual_seed(1234)
+    got = mod(x=cam, roi=roi)
+    torch.manual_seed(1234)
+    want = ref.tcam_seeder_forward(cam, roi, seed_tech=mod.seed_tech, min_=mod.min_, max_=mod.max_, min_p=mod.min_p,
+                                   max_p=mod.max_p, ksz=mod.ksz, ignore_idx=-255, use_roi=mod.use_roi)
+    assert got.dtype == torch.long and got.shape == (b, h, w)
+    assert torch.equal(got, want)
+    assert (got[1] == -255).all()
+    # and the two random streams are at the same position afterwards
+    assert torch.equal(torch.rand(4, device="cuda"), torch.rand(4, device="cuda")) is False
+    torch.manual_seed(1234)
+    mod(x=cam, roi=roi)
+    a = torch.rand(4, device="cuda")
+    torch.manual_seed(1234)
+    ref.tcam_seeder_forward(cam, roi, seed_tech=mod.seed_tech, min_=mod.min_, max_=mod.max_, min_p=mod.min_p,
+                            max_p=mod.max_p, ksz=mod.ksz, ignore_idx=-255, use_roi=mod.use_roi)
+    assert torch.equal(a, torch.rand(4, device="cuda"))
+
+
+def test_ties_follow_stable_sort_order(torch_cuda):
+    """Heavily quantised CAMs: most of the n-th values tie, and a stable sort keeps the lower pixel index."""
+    torch = torch_cuda
+    from oracle import seeding as ref
+    b, h, w = 3, 64, 48
+    g = torch.Generator().manual_seed(3)
+    cam = (torch.randint(0, 4, (b, 1, h, w), generator=g).float() / 4).cuda()
+    roi = (torch.rand((b, 1, h, w), generator=g) > 0.3).long().cuda()
+    for tech in ("seed_weighted", "seed_uniform"):
+        mod = _seeder(seed_tech=tech, min_=4, max_=4, ksz=1)
+        torch.manual_seed(7)
+        got = mod(x=cam, roi=roi)
+        torch.manual_seed(7)
+        want = ref.tcam_seeder_forward(cam, roi, seed_tech=tech, min_=4, max_=4, min_p=0.1, max_p=0.6, ksz=1,
+                                       ignore_idx=-255, use_roi=True)
+        assert torch.equal(got, want)
+
+
+def test_fused_temporal_max_and_seeding(torch_cuda):
+    """BASELINE configs[2]: max over the current + 4 previous frames' CAMs fused with seeding == max chain
+    followed by the reference seeder."""
+    torch = torch_cuda
+    from oracle import seeding as ref
+    b, t, h, w = 32, 5, 224, 224
+    low = torch.from_numpy(synth.make_low_res_cams(b, t, 28, 28, seed=0)).squeeze(2)       # [B,T,28,28]
+    cams = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False).cuda()
+    cam_max_want = ref.temporal_max(cams)
+    roi = (cam_max_want >= 0.5).long().unsqueeze(1)
+    mod = _seeder()
+    torch.manual_seed(99)
+    got, cam_max = mod.forward_stack(cams, roi)
+    torch.manual_seed(99)
+    want = ref.tcam_seeder_forward(cam_max_want.unsqueeze(1), roi, seed_tech=mod.seed_tech, min_=1, max_=1,
+                                   min_p=0.1, max_p=0.6, ksz=3, ignore_idx=-255, use_roi=True)
+    assert torch.equal(cam_max, cam_max_want)
+    assert torch.equal(got, want)
+    assert int((got == 1).sum()) > 0 and int((got == 0).sum()) > 0
+
+
+def test_seeder_api_surface(torch_cuda):
+    torch = torch_cuda
+    mod = _seeder()
+    assert "min_=1, max_=1, min_p=0.1,max_p=0.6, ksz=3, fg_erode_k: 11, fg_erode_iter: 0" in mod.extra_repr()
+    mod.set_seed_tech("seed_uniform")
+    assert mod.seed_tech == "seed_uniform"
+    cam, roi = _make(torch, 2, 32, 32, seed=1)
+    out = mod.use_all_roi(cam, roi)
+    assert torch.equal(out == 1, roi.squeeze(1) == 1) and ((out == 1) | (out == -255)).all()
+    with pytest.raises(NotImplementedError):
+        mod(x=cam, roi=None)
+    # erosion of the roi before sampling (fg_erode_iter > 0) keeps seeds inside the eroded region
+    mod = _seeder(fg_erode_k=5, fg_erode_iter=1, ksz=1, max_=8)
+    seeds = mod(x=cam, roi=roi)
+    eroded = mod._erode(roi).squeeze(1)
+    assert ((seeds == 1) <= (eroded == 1)).all()
