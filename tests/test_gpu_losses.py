@@ -1,0 +1,103 @@
+"""GPU suite (-m gpu): the loss-side callers (tcam_wsol_video_b200/losses.py) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from tcam_wsol_video_b200 import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def test_con_ran_field_tcams(torch_cuda, oracle_mod):
+    torch = torch_cuda
+    from tcam_wsol_video_b200.losses import ConRanFieldTcams
+    n, k, h, w = 4, 2, 48, 56
+    raw = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=3))            # CPU, 0..255
+    logits = torch.randn((n, k, h, w), generator=torch.Generator().manual_seed(3)).cuda().requires_grad_(True)
+    mod = ConRanFieldTcams(cuda_id=0, lambda_=2e-9, sigma_rgb=15., sigma_xy=100., scale_factor=1.0,
+                           start_epoch=2, end_epoch=-1)
+    assert mod.__name__ == "con_ran_field_tcams"
+    off = mod(epoch=1, fcams=logits, raw_img=raw)
+    assert off.item() == 0.0                                                           # before start_epoch
+    loss = mod(epoch=2, fcams=logits, raw_img=raw)
+    loss.backward()
+    probs = torch.softmax(logits.detach().cpu(), dim=1)
+    want, want_grad, _ = oracle_mod.densecrf_loss_fwd_bwd(raw.numpy(), probs.numpy(), 15., 100., 2e-9,
+                                                          oracle_mod.port_bilateralfilter_batch)
+    assert abs(loss.item() - 2e-9 * float(want)) < REL_TOL * abs(2e-9 * float(want))
+    # chain rule through the softmax, done by torch on both sides
+    p = torch.softmax(logits.detach().cpu().requires_grad_(True), dim=1)
+    ref_logits = logits.detach().cpu().requires_grad_(True)
+    torch.softmax(ref_logits, dim=1).backward(torch.from_numpy(want_grad))
+    assert rel_err(logits.grad.cpu().numpy(), ref_logits.grad.numpy()) < REL_TOL
+    # single-channel map -> (1-sigmoid, sigmoid)
+    one = torch.randn((n, 1, h, w), generator=torch.Generator().manual_seed(4)).cuda()
+    l1 = mod(epoch=5, fcams=one, raw_img=raw)
+    s = torch.sigmoid(one.cpu())
+    w1, _, _ = oracle_mod.densecrf_loss_fwd_bwd(raw.numpy(), torch.cat((1 - s, s), 1).numpy(), 15., 100., 1.0,
+                                                oracle_mod.port_bilateralfilter_batch)
+    assert abs(l1.item() - 2e-9 * float(w1)) < REL_TOL * abs(2e-9 * float(w1))
+
+
+def test_rgb_joint_con_ran_field_tcams(torch_cuda, oracle_mod):
+    """Clips of 3 and 2 frames plus a singleton (skipped): batched per-clip lattices == the reference's
+    per-clip loop over width-concatenated frames, averaged over clips (tcam.py:191-205)."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.losses import RgbJointConRanFieldTcams, group_ordered_frames
+    h, w, k = 24, 32, 2
+    seq = torch.tensor([7, 3, 7, 3, 7, 9, 3, 4, 4])
+    frm = torch.tensor([2, 0, 0, 2, 1, 5, 1, 1, 0])
+    n = len(seq)
+    raw = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=8))
+    logits = torch.randn((n, k, h, w), generator=torch.Generator().manual_seed(8)).cuda().requires_grad_(True)
+    groups = group_ordered_frames(seq, frm)
+    assert groups == [[1, 6, 3], [8, 7], [2, 4, 0], [5]]
+    mod = RgbJointConRanFieldTcams(cuda_id=0, lambda_=1e-6, sigma_rgb=15., scale_factor=1.0)
+    loss = mod(epoch=0, fcams=logits, raw_img=raw, seq_iter=seq, frm_iter=frm)
+    loss.backward()
+    probs = torch.softmax(logits.detach().cpu(), dim=1).numpy()
+    total, grads = 0.0, np.zeros_like(probs)
+    clips = [g for g in groups if len(g) >= 2]
+    for g in clips:
+        img = np.concatenate([raw.numpy()[i] for i in g], axis=2)[None]      # width concat
+        seg = np.concatenate([probs[i] for i in g], axis=2)[None]
+        l, gr, _ = oracle_mod.color_densecrf_loss_fwd_bwd(img, seg, 15., 1e-6 / len(clips),
+                                                          oracle_mod.port_colorbilateralfilter_batch)
+        total += 1e-6 * float(l) / len(clips)
+        for j, i in enumerate(g):
+            grads[i] = gr[0][:, :, j * w:(j + 1) * w]
+    assert abs(loss.item() - total) < REL_TOL * abs(total)
+    ref_logits = logits.detach().cpu().requires_grad_(True)
+    torch.softmax(ref_logits, dim=1).backward(torch.from_numpy(grads))
+    assert rel_err(logits.grad.cpu().numpy(), ref_logits.grad.numpy()) < REL_TOL
+    # pair_samples keeps the reference signature
+    pi, pc = mod.pair_samples([2, 4, 0], raw, torch.from_numpy(probs))
+    assert pi.shape == (1, 3, h, 3 * w) and pc.shape == (1, k, h, 3 * w)
+    assert torch.equal(pi[0, :, :, w:2 * w], raw[4])
+
+
+def test_self_learning_tcams_consumes_seeds(torch_cuda):
+    torch = torch_cuda
+    from tcam_wsol_video_b200.losses import SelfLearningTcams
+    from tcam_wsol_video_b200.tcam_seeding import TCAMSeeder
+    b, h, w = 4, 64, 64
+    cam = torch.rand((b, 1, h, w), generator=torch.Generator().manual_seed(2)).cuda()
+    roi = (cam > 0.5).long()
+    seeder = TCAMSeeder(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11,
+                        fg_erode_iter=0, ksz=3, support_background=True, multi_label_flag=False,
+                        seg_ignore_idx=-255, cuda_id=0, roi_method="roi_all", p_min_area_roi=0.05, use_roi=True)
+    seeds = seeder(x=cam, roi=roi)
+    fcams = torch.randn((b, 2, h, w), device="cuda", requires_grad=True)
+    loss = SelfLearningTcams(cuda_id=0, lambda_=1.0, seg_ignore_idx=-255)(epoch=0, fcams=fcams, seeds=seeds)
+    want = torch.nn.functional.cross_entropy(fcams, seeds, ignore_index=-255)
+    assert torch.allclose(loss, want)
+    loss.backward()
+    assert int((seeds >= 0).sum()) <= b * 2 * 9 and fcams.grad.abs().sum() > 0
