@@ -153,6 +153,9 @@ def cpu_fwd_bwd_frames_per_sec(frames: int, K: int, kind: str, reps: int, warmup
     seg = synth.make_segs(frames, K, H, W, seed=0)
     cores = len(os.sched_getaffinity(0))
     if which == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; give the reference every host core it is allowed to use
+        # (its own code then takes min(max_threads, N), bilateralfilter.cpp:45-47)
+        oracle.ref_set_threads(cores)
         threads = min(oracle.load_ref()[0].ref_omp_max_threads(), frames)
     else:
         threads = 1
@@ -171,6 +174,11 @@ def run_reference(args, rank: int, world: int):
         return
     frames = args.frames
     t0 = time.perf_counter()
+    # bounded sample: keep the whole run within ~150 s whatever --steps is (calibrate on a few frames)
+    cal = min(frames, max(2, len(os.sched_getaffinity(0))))
+    _, cal_fps, *_ = cpu_fwd_bwd_frames_per_sec(cal, args.classes, args.kind, reps=1, warmup=0)
+    budget_frames = int(150.0 * cal_fps / max(args.steps + args.warmup, 1))
+    frames = max(1, min(frames, budget_frames))
     best, mean, which, threads, cores, times = cpu_fwd_bwd_frames_per_sec(frames, args.classes, args.kind,
                                                                           reps=max(args.steps, 1),
                                                                           warmup=max(args.warmup, 0))
@@ -188,7 +196,7 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -366,10 +374,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # libraries that print to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
