@@ -34,6 +34,7 @@
 //     rel 1e-4; measured ~1e-6).  Blur and slice round exactly like the SSE code.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -1275,8 +1276,13 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     int rc = check_device();
     if (rc) return rc;
     if (!cfg_in || !images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
-    // frames per pipeline group: ~8 groups, each still large enough to fill the GPU
-    int group = (N + 7) / 8;
+    // frames per pipeline group: a few groups, each still large enough to fill the GPU
+    int want_groups = K >= 6 ? 6 : 4;   // measured on B200 (tools/e2e_sweep.sh): K=10 best at 6, K=2 at 4
+    if (const char *env = getenv("TCAMCRF_HOST_GROUPS")) {
+        const int v = atoi(env);
+        if (v >= 1 && v <= 64) want_groups = v;
+    }
+    int group = (N + want_groups - 1) / want_groups;
     if (group < 1) group = 1;
     const int ngroups = (N + group - 1) / group;
     tcamcrf_config cfg = *cfg_in;
