@@ -5,7 +5,7 @@
 //   prepare_kernel       clears the primary tier of the frame tables (and the overflow
 //                        tier only if the previous use spilled into it), zeroes counters
 //   build_kernel<D>      per pixel: features -> embedding -> d+1 packed keys ->
-//                        warp-deduplicated insert into the frame's two-tier table
+//                        warp-deduplicated (runs of equal keys) insert into the frame's two-tier table
 //                        (all first probes issued before any is consumed);
 //                        block-aggregated allocation of dense, per-frame-contiguous ids
 //   vertex_init_kernel   zeroes the value rows of the vertices in use, presets links to "missing"
@@ -132,16 +132,7 @@ struct StageScope {
 // ---------------------------------------------------------------------------
 constexpr int kThreads = 256;
 
-// tuning knobs (items a thread keeps in flight per loop iteration); see profiles/README.md for the sweeps
-#ifndef TCAMCRF_NBR_U
-#define TCAMCRF_NBR_U 1
-#endif
-#ifndef TCAMCRF_NBR_BOTH
-#define TCAMCRF_NBR_BOTH 0
-#endif
-#ifndef TCAMCRF_BLUR_U
-#define TCAMCRF_BLUR_U 1
-#endif
+
 
 // ctrl words (ints).  [0,16) are reset by the host at the start of every call; MAGIC/DIRTY persist
 // with the workspace; per-frame vertex counters follow at kCtrlCounts.
@@ -224,6 +215,8 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     if (pl.pool > 0x7fffff00ll) return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
     if ((unsigned long long)pl.slots * pl.chunk > 0x7fffff00ull)
         return fail(TCAMCRF_ERR_INVALID, "hash tables too large; lower chunk_frames");
+    if (pl.pool * (D + 1) > 0x7fffff00ll)
+        return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
     // + 1: the ghost pixel that stands for the reference's zero-feature padding (see build_kernel)
     pl.blocks_per_frame = (pl.P + 1 + kThreads - 1) / kThreads;
     unsigned int sig = 0x9e3779b9u;
@@ -372,10 +365,13 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
     }
     if (!ok) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_KEY_RANGE);
 
-    // Warp-cooperative insertion.  Lanes holding the same key elect one leader; only leaders touch the
-    // table and the entry index is broadcast back.  A leader probes for all the keys it leads in lock
-    // step: every round issues one load per pending key before any result is consumed, so the d+1
-    // dependent probe chains overlap instead of running one after the other.
+    // Warp-cooperative insertion.  A warp holds 32 neighbouring pixels of one image row; in real frames
+    // most of them fall on the same lattice vertices.  Lanes whose key equals their left neighbour's form a
+    // run; only the head of a run touches the table and the entry index is broadcast back to the run
+    // (one SHFL + one ballot per key -- MATCH.ANY.U64 measured ~3x the short-scoreboard stalls; equal keys
+    // that are not adjacent are simply inserted twice, the second insert finds the first).  A head probes
+    // for all the keys it leads in lock step: every round issues one load per pending key before any result
+    // is consumed, so the d+1 dependent probe chains overlap instead of running one after the other.
     Entry *tab = p.table + (size_t)n * p.slots;
     const unsigned int mask1 = p.geom.slots1 - 1;
     unsigned int pend = 0;
@@ -384,12 +380,14 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
     unsigned long long cur[D + 1];
 #pragma unroll
     for (int r = 0; r <= D; r++) {
-        const unsigned int peers = __match_any_sync(0xffffffffu, key[r]);
-        leader[r] = __ffs(peers) - 1;
+        const unsigned long long left = __shfl_up_sync(0xffffffffu, key[r], 1);
+        const bool head = lane == 0 || left != key[r];
+        const unsigned int heads = __ballot_sync(0xffffffffu, head);
+        leader[r] = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // nearest head at or below this lane
         hh[r] = 0;
         cur[r] = 0;
         slot[r] = -1;
-        if (active && lane == leader[r]) {
+        if (active && head) {
             pend |= 1u << r;
             hh[r] = (unsigned int)hash_key(key[r]) & mask1;
             cur[r] = load_key_cg(tab + hh[r]);
@@ -542,128 +540,75 @@ __device__ __forceinline__ int find_frame(const int *s_prefix, int nc, int t)
     return lo;
 }
 
+// A thread's flat index only grows from one loop iteration to the next, so the frame can be tracked with a
+// cursor that moves forward (amortised O(1)) instead of a binary search per item.
+__device__ __forceinline__ int advance_frame(const int *s_prefix, int nc, int n, int t)
+{
+    while (n + 1 < nc && t >= s_prefix[n + 1]) n++;
+    return n;
+}
+
 // Zeroes the value rows and presets every neighbour link of the vertices in use to "missing".
 __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int dp1, int nc)
 {
     __shared__ int s_prefix[kMaxChunk + 1];
-    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
-    // value rows, one float4 at a time (Kp is 1, 2 or a multiple of 4; rows of a frame start 16-byte aligned)
-    if ((p.Kp & 3) == 0) {
-        const int q = p.Kp >> 2;
-        for (long long i = tid; i < (long long)total * q; i += stride) {
-            const int t = (int)(i / q);
-            const int n = find_frame(s_prefix, nc, t);
-            const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
-            reinterpret_cast<float4 *>(p.values + v * p.Kp)[i - (long long)t * q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
+    const int stride = gridDim.x * kThreads;
+    const int tid = blockIdx.x * kThreads + threadIdx.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int4 none4 = make_int4(-1, -1, -1, -1);
+    // pure streaming stores: walk the frames one after the other (the counts sit in shared memory), 16 bytes
+    // per store; a frame's rows start 16-byte aligned (stride is a multiple of 32) and a store may run up to
+    // 12 bytes past the last vertex in use, into rows nothing reads
+    for (int n = 0; n < nc; n++) {
+        const int M = s_prefix[n + 1] - s_prefix[n];
+        const size_t id0 = (size_t)n * p.stride;
+        float4 *v4 = reinterpret_cast<float4 *>(p.values + id0 * p.Kp);
+        const int quads = (M * p.Kp + 3) >> 2;
+        for (int i = tid; i < quads; i += stride) v4[i] = zero4;
+        const int pairs = (M + 1) >> 1;
+        for (int j = 0; j < dp1; j++) {
+            int4 *l4 = reinterpret_cast<int4 *>(p.nbr + (size_t)j * p.pool + id0);
+            for (int i = tid; i < pairs; i += stride) l4[i] = none4;
         }
-    } else {
-        for (long long i = tid; i < (long long)total * p.Kp; i += stride) {
-            const int t = (int)(i / p.Kp);
-            const int n = find_frame(s_prefix, nc, t);
-            const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
-            p.values[v * p.Kp + (i - (long long)t * p.Kp)] = 0.f;
-        }
-    }
-#if TCAMCRF_NBR_BOTH
-    return;
-#endif
-    const int2 none = make_int2(-1, -1);
-    for (long long i = tid; i < (long long)total * dp1; i += stride) {
-        const int j = (int)(i / total);
-        const int t = (int)(i - (long long)j * total);
-        const int n = find_frame(s_prefix, nc, t);
-        const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
-        p.nbr[(size_t)j * p.pool + v] = none;
     }
 }
 
 // Blur neighbours.  n1(v, j) = u  <=>  n2(u, j) = v, so ONE lookup per (vertex, axis) fills both directions;
-// every link was preset to -1 by vertex_init_kernel.  Each thread handles kU (vertex, axis) items at a
-// time: their key loads and first probes are issued together so the dependent round trips overlap.
+// every link was preset to -1 by vertex_init_kernel.  (Keeping several items per thread in flight, or looking
+// both neighbours up instead of scattering the symmetric link, measured no faster: profiles/README.md.)
 template <int D>
 __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams p, int nc)
 {
     using Codec = KeyCodec<D>;
-    constexpr int kU = TCAMCRF_NBR_U;
     __shared__ int s_prefix[kMaxChunk + 1];
     const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const int stride = gridDim.x * kThreads;
+    const int tid = blockIdx.x * kThreads + threadIdx.x;
     const unsigned int mask1 = p.geom.slots1 - 1;
-    const long long work = (long long)total * (D + 1);
+    const int work = total * (D + 1);   // < 2^31: pool * (D+1) is checked in make_plan
     // items are ordered frame by frame (so the grid probes one or two frame tables at a time and they stay
     // in L2), axis-major inside a frame: adjacent lanes handle adjacent vertices of one axis (coalesced key
     // loads and link stores)
-    for (long long base = tid; base < work; base += stride * kU) {
-        int id[kU], axis[kU];
-        const Entry *tab[kU];
-        unsigned long long k1[kU];
-        unsigned int h[kU];
-        uint4 e[kU];
-        unsigned long long key[kU];
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            const long long i = base + u * stride;
-            axis[u] = -1;
-            id[u] = 0;
-            key[u] = 0;
-            tab[u] = p.table;
-            if (i < work) {
-                const int n = find_frame(s_prefix, nc, (int)(i / (D + 1)));   // prefix[n]*(D+1) <= i
-                const int m = s_prefix[n + 1] - s_prefix[n];
-                const int local = (int)(i - (long long)s_prefix[n] * (D + 1));
-                axis[u] = local / m;
-                id[u] = n * p.stride + (local - axis[u] * m);
-                tab[u] = p.table + (size_t)n * p.slots;
-                key[u] = __ldg(p.vkey + id[u]);
-            }
+    int n = 0;
+    for (int i = tid; i < work; i += stride) {
+        n = advance_frame(s_prefix, nc, n, i / (D + 1));   // prefix[n]*(D+1) <= i
+        const int m = s_prefix[n + 1] - s_prefix[n];
+        const int local = i - s_prefix[n] * (D + 1);
+        const int axis = local / m;
+        const int id = n * p.stride + (local - axis * m);
+        const Entry *tab = p.table + (size_t)n * p.slots;
+        const unsigned long long key = __ldg(p.vkey + id);
+        unsigned long long k1, k2;
+        Codec::neighbour_keys(key, axis, k1, k2);
+        const unsigned int h = (unsigned int)hash_key(k1) & mask1;
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
+        const int nb = table_lookup_from(tab, p.geom, k1, h, 0, e);
+        if (nb >= 0) {
+            int2 *row = p.nbr + (size_t)axis * p.pool;
+            row[id].x = nb;
+            row[nb].y = id;
         }
-#if TCAMCRF_NBR_BOTH
-        // variant: look both neighbours up, one coalesced int2 store, no scattered stores, no link preset
-        unsigned long long k2[kU];
-        unsigned int h2[kU];
-        uint4 e2[kU];
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            Codec::neighbour_keys(key[u], axis[u] < 0 ? 0 : axis[u], k1[u], k2[u]);
-            h[u] = (unsigned int)hash_key(k1[u]) & mask1;
-            h2[u] = (unsigned int)hash_key(k2[u]) & mask1;
-            e[u] = e2[u] = make_uint4(0, 0, 0, 0);
-            if (axis[u] >= 0) {
-                e[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h[u]));
-                e2[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h2[u]));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            if (axis[u] < 0) continue;
-            int2 out;
-            out.x = table_lookup_from(tab[u], p.geom, k1[u], h[u], 0, e[u]);
-            out.y = table_lookup_from(tab[u], p.geom, k2[u], h2[u], 0, e2[u]);
-            p.nbr[(size_t)axis[u] * p.pool + id[u]] = out;
-        }
-#else
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            unsigned long long k2;
-            Codec::neighbour_keys(key[u], axis[u] < 0 ? 0 : axis[u], k1[u], k2);
-            h[u] = (unsigned int)hash_key(k1[u]) & mask1;
-            e[u] = make_uint4(0, 0, 0, 0);
-            if (axis[u] >= 0) e[u] = __ldg(reinterpret_cast<const uint4 *>(tab[u] + h[u]));
-        }
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            if (axis[u] < 0) continue;
-            const int nb = table_lookup_from(tab[u], p.geom, k1[u], h[u], 0, e[u]);
-            if (nb >= 0) {
-                int2 *row = p.nbr + (size_t)axis[u] * p.pool;
-                row[id[u]].x = nb;
-                row[nb].y = id[u];
-            }
-        }
-#endif
     }
     if (tid == 0) {
         p.ctrl[kCtrlLastCount] = total;
@@ -772,57 +717,32 @@ struct BlurParams {
     int Kp, stride;
 };
 
-// persistent 1-D grid over the flat vertex list (see the note above load_frame_prefix); kU items per thread
-// per iteration so that the neighbour-id loads and the two gathers of several items are in flight together
+// persistent 1-D grid over the flat, frame-ordered vertex list (see the note above load_frame_prefix)
 template <int V>
 __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int nc)
 {
-    constexpr int kU = TCAMCRF_BLUR_U;
     __shared__ int s_prefix[kMaxChunk + 1];
     const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
     const int kv = p.Kp / V;
     const long long work = (long long)total * kv;
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long base = (long long)blockIdx.x * kThreads + threadIdx.x; base < work; base += stride * kU) {
-        size_t v[kU];
-        int c[kU];
-        int2 nb[kU];
-        bool on[kU];
+    int n = 0;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < work; i += stride) {
+        const int t = (int)(i / kv);
+        const int c = (int)(i - (long long)t * kv) * V;
+        n = advance_frame(s_prefix, nc, n, t);
+        const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
+        const int2 nb = __ldg(p.nbr + v);
+        float own[V], a[V], b[V], out[V];
+        load_vec<V>(p.src + v * p.Kp + c, own);
 #pragma unroll
-        for (int u = 0; u < kU; u++) {
-            const long long i = base + u * stride;
-            on[u] = i < work;
-            v[u] = 0;
-            c[u] = 0;
-            nb[u] = make_int2(-1, -1);
-            if (on[u]) {
-                const int t = (int)(i / kv);
-                c[u] = (int)(i - (long long)t * kv) * V;
-                const int n = find_frame(s_prefix, nc, t);
-                v[u] = (size_t)n * p.stride + (t - s_prefix[n]);
-                nb[u] = __ldg(p.nbr + v[u]);
-            }
-        }
-        float own[kU][V], a[kU][V], b[kU][V];
+        for (int e = 0; e < V; e++) a[e] = b[e] = 0.f;
+        if (nb.x >= 0) load_vec<V>(p.src + (size_t)nb.x * p.Kp + c, a);
+        if (nb.y >= 0) load_vec<V>(p.src + (size_t)nb.y * p.Kp + c, b);
+        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
 #pragma unroll
-        for (int u = 0; u < kU; u++) {
-#pragma unroll
-            for (int e = 0; e < V; e++) own[u][e] = a[u][e] = b[u][e] = 0.f;
-            if (on[u]) {
-                load_vec<V>(p.src + v[u] * p.Kp + c[u], own[u]);
-                if (nb[u].x >= 0) load_vec<V>(p.src + (size_t)nb[u].x * p.Kp + c[u], a[u]);
-                if (nb[u].y >= 0) load_vec<V>(p.src + (size_t)nb[u].y * p.Kp + c[u], b[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            if (!on[u]) continue;
-            float out[V];
-            // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
-#pragma unroll
-            for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[u][e], __fmul_rn(0.5f, __fadd_rn(a[u][e], b[u][e])));
-            store_vec<V>(p.dst + v[u] * p.Kp + c[u], out);
-        }
+        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
+        store_vec<V>(p.dst + v * p.Kp + c, out);
     }
 }
 
