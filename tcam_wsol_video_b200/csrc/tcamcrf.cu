@@ -681,30 +681,59 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
 {
     const int n = blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
-    if (pix >= p.P) return;
-    const size_t base = (size_t)n * (D + 1) * p.P + pix;
+    const bool valid = pix < p.P;
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)n * (D + 1) * p.P + (valid ? pix : 0);
     int id[D + 1];
     float w[D + 1];
+    // Runs of neighbouring lanes that hit the same vertex (the common case in real frames: ~100 pixels per
+    // vertex) are summed in registers first and only the head of a run issues the RED -- same-address atomics
+    // serialise in L2.  run[r] = lanes above this one (bit i = lane+1+i) up to the end of its run.
+    unsigned int heads[D + 1];
+    bool any_run = false;
 #pragma unroll
     for (int r = 0; r <= D; r++) {
-        const int s = p.offset[base + (size_t)r * p.P];
-        const int v = s < 0 ? -1 : __ldg(&p.table[s].id);
+        int v = -1;
+        if (valid) {
+            const int s = p.offset[base + (size_t)r * p.P];
+            v = s < 0 ? -1 : __ldg(&p.table[s].id);
+            p.offset[base + (size_t)r * p.P] = v;
+            w[r] = p.bary[base + (size_t)r * p.P];
+        } else {
+            w[r] = 0.f;
+        }
         id[r] = v;
-        p.offset[base + (size_t)r * p.P] = v;
-        w[r] = p.bary[base + (size_t)r * p.P];
+        const int left = __shfl_up_sync(0xffffffffu, v, 1);
+        const bool head = lane == 0 || left != v;
+        heads[r] = __ballot_sync(0xffffffffu, head);
+        any_run |= heads[r] != 0xffffffffu;
     }
-    const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
+    const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
     for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = (k + e < p.K) ? __ldg(seg + (size_t)(k + e) * p.P) : 0.f;
+        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? __ldg(seg + (size_t)(k + e) * p.P) : 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
-            if (id[r] < 0) continue;
             float t[V];
 #pragma unroll
             for (int e = 0; e < V; e++) t[e] = __fmul_rn(w[r], s[e]);
-            red_add(p.values + (size_t)id[r] * p.Kp + k, t);
+            bool issue = id[r] >= 0;
+            if (any_run && heads[r] != 0xffffffffu) {   // warp-uniform: some run of this remainder is longer than 1
+                // segmented suffix sum over the run: lane i adds lane i+o when no head lies in (i, i+o]
+                const unsigned int above = heads[r] >> 1 >> lane;   // bit j = head flag of lane+1+j
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const bool take = (lane + o < 32) && ((above & ((1u << o) - 1u)) == 0u);
+#pragma unroll
+                    for (int e = 0; e < V; e++) {
+                        const float other = __shfl_down_sync(0xffffffffu, t[e], o);
+                        if (take) t[e] += other;
+                    }
+                }
+                issue = issue && ((heads[r] >> lane) & 1u);
+            }
+            if (issue) red_add(p.values + (size_t)id[r] * p.Kp + k, t);
         }
     }
 }
