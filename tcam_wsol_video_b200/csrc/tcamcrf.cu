@@ -7,7 +7,7 @@
 //   build_kernel<D>      per pixel: features -> embedding -> d+1 packed keys ->
 //                        warp-deduplicated (runs of equal keys) insert into the frame's two-tier table
 //                        (all first probes issued before any is consumed);
-//                        block-aggregated allocation of dense, per-frame-contiguous ids
+//                        warp-aggregated allocation of dense, per-frame-contiguous ids
 //   vertex_init_kernel   zeroes the value rows of the vertices in use, presets links to "missing"
 //   neighbour_kernel<D>  per (vertex, axis): ONE table lookup (the n1 neighbour); the
 //                        symmetric n2 link is written from the other side
@@ -308,13 +308,19 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
     if (tid == 0) ctrl[kCtrlLastCount] = 0;
 }
 
+// Occupancy target of the build kernel: 5 blocks of 256 threads per SM caps it at 48 registers (a few
+// spills).  Measured on B200 (K=2, noise / natural frames, ms per 32-frame batch): 3 blocks 0.250 / 0.143,
+// 4 blocks 0.221 / 0.119, 5 blocks 0.214 / 0.109, 6 blocks 0.218 / 0.107, 8 blocks 0.235 / 0.107.
+#ifndef TCAMCRF_BUILD_MINBLOCKS
+#define TCAMCRF_BUILD_MINBLOCKS 5
+#endif
+#ifndef TCAMCRF_BLUR_U
+#define TCAMCRF_BLUR_U 1
+#endif
 template <int D, typename ImgT>
-__global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
+__global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kernel(const BuildParams p)
 {
     using Codec = KeyCodec<D>;
-    __shared__ int s_warp[kThreads / 32];
-    __shared__ int s_base;
-
     const int n = blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
     const bool valid = pix < p.P;
@@ -435,7 +441,8 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
     if (table_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_TABLE_FULL);
     if (spilled_any) p.ctrl[kCtrlDirtyNew] = 1;
 
-    // block-aggregated allocation of dense vertex ids: one atomic per block on the frame's counter
+    // warp-aggregated allocation of dense vertex ids: one atomic per warp on the frame's counter (no block
+    // barrier: a warp that is done does not wait for the slowest warp of its block)
     const int nwin = __popc(wonmask);
     int incl = nwin;
 #pragma unroll
@@ -443,21 +450,10 @@ __global__ void __launch_bounds__(kThreads) build_kernel(const BuildParams p)
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    const int warp = threadIdx.x >> 5;
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int total = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) {
-            const int t = s_warp[w];
-            s_warp[w] = total;
-            total += t;
-        }
-        s_base = total > 0 ? atomicAdd(p.ctrl + kCtrlCounts + n, total) : 0;
-    }
-    __syncthreads();
-    int local = s_base + s_warp[warp] + incl - nwin;
+    int wbase = 0;
+    if (lane == 31 && incl > 0) wbase = atomicAdd(p.ctrl + kCtrlCounts + n, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    int local = wbase + incl - nwin;
     bool pool_full = false;
 #pragma unroll
     for (int r = 0; r <= D; r++) {
@@ -746,32 +742,56 @@ struct BlurParams {
     int Kp, stride;
 };
 
-// persistent 1-D grid over the flat, frame-ordered vertex list (see the note above load_frame_prefix)
+// persistent 1-D grid over the flat, frame-ordered vertex list (see the note above load_frame_prefix);
+// TCAMCRF_BLUR_U items per thread and iteration (their link loads, then their gathers, are issued together)
 template <int V>
 __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int nc)
 {
+    constexpr int kU = TCAMCRF_BLUR_U;
     __shared__ int s_prefix[kMaxChunk + 1];
     const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
     const int kv = p.Kp / V;
     const long long work = (long long)total * kv;
     const long long stride = (long long)gridDim.x * kThreads;
     int n = 0;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < work; i += stride) {
-        const int t = (int)(i / kv);
-        const int c = (int)(i - (long long)t * kv) * V;
-        n = advance_frame(s_prefix, nc, n, t);
-        const size_t v = (size_t)n * p.stride + (t - s_prefix[n]);
-        const int2 nb = __ldg(p.nbr + v);
-        float own[V], a[V], b[V], out[V];
-        load_vec<V>(p.src + v * p.Kp + c, own);
+    for (long long base = (long long)blockIdx.x * kThreads + threadIdx.x; base < work; base += stride * kU) {
+        size_t v[kU];
+        int c[kU];
+        int2 nb[kU];
 #pragma unroll
-        for (int e = 0; e < V; e++) a[e] = b[e] = 0.f;
-        if (nb.x >= 0) load_vec<V>(p.src + (size_t)nb.x * p.Kp + c, a);
-        if (nb.y >= 0) load_vec<V>(p.src + (size_t)nb.y * p.Kp + c, b);
-        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
+        for (int u = 0; u < kU; u++) {
+            const long long i = base + u * stride;
+            v[u] = 0;
+            c[u] = -1;
+            nb[u] = make_int2(-1, -1);
+            if (i < work) {
+                const int t = (int)(i / kv);
+                c[u] = (int)(i - (long long)t * kv) * V;
+                n = advance_frame(s_prefix, nc, n, t);
+                v[u] = (size_t)n * p.stride + (t - s_prefix[n]);
+                nb[u] = __ldg(p.nbr + v[u]);
+            }
+        }
+        float own[kU][V], a[kU][V], b[kU][V];
 #pragma unroll
-        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
-        store_vec<V>(p.dst + v * p.Kp + c, out);
+        for (int u = 0; u < kU; u++) {
+#pragma unroll
+            for (int e = 0; e < V; e++) own[u][e] = a[u][e] = b[u][e] = 0.f;
+            if (c[u] >= 0) {
+                load_vec<V>(p.src + v[u] * p.Kp + c[u], own[u]);
+                if (nb[u].x >= 0) load_vec<V>(p.src + (size_t)nb[u].x * p.Kp + c[u], a[u]);
+                if (nb[u].y >= 0) load_vec<V>(p.src + (size_t)nb[u].y * p.Kp + c[u], b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            if (c[u] < 0) continue;
+            float out[V];
+            // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
+#pragma unroll
+            for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[u][e], __fmul_rn(0.5f, __fadd_rn(a[u][e], b[u][e])));
+            store_vec<V>(p.dst + v[u] * p.Kp + c[u], out);
+        }
     }
 }
 
