@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--rotate", type=int, default=4, help="distinct input batches cycled through (defeats L2 reuse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs on the other input regimes")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 -> min(steps, 20)")
     return ap.parse_args()
 
@@ -322,6 +323,28 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "tcamcrf_loss_fwd_bwd_host (host pointers in, loss + gradient out)"}
 
+    # ---- the same step on the other input regimes (short, device-resident; context for the headline number)
+    extra = {}
+    if world == 1 and not args.no_extra:
+        for kind, k in (("natural", K), ("noise", 2), ("natural", 2)):
+            if kind == args.kind and k == K:
+                continue
+            img = torch.from_numpy(synth.make_images(N, H, W, kind, seed=7)).to(dev)
+            seg = torch.from_numpy(synth.make_segs(N, k, H, W, seed=7)).to(dev).requires_grad_(True)
+            for _ in range(5):
+                seg.grad = None
+                crf(images=img, segmentations=seg).backward()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(30):
+                seg.grad = None
+                crf(images=img, segmentations=seg).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            extra[f"{kind}_k{k}"] = {"value": N * 30 / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "steps": 30}
+            del img, seg
+
     if rank != 0:
         return
 
@@ -374,7 +397,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary(), "other_inputs": extra,
     }
     emit(line)
 
