@@ -160,7 +160,7 @@ def test_lattice_structure_bit_exact(torch_cuda, oracle_mod, kind, dim, hw):
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["noise", "natural"])
 @pytest.mark.parametrize("shape", [(1, 2, 224, 224), (3, 10, 64, 48), (2, 1, 33, 35), (2, 3, 17, 129), (1, 4, 1, 1),
-                                   (2, 2, 1, 50), (1, 5, 3, 2)])
+                                   (2, 2, 1, 50), (1, 5, 3, 2), (1, 2, 448, 448)])
 def test_filter_vs_oracle(torch_cuda, oracle_mod, kind, shape):
     n, k, h, w = shape
     img = synth.make_images(n, h, w, kind, seed=31)
@@ -357,6 +357,43 @@ def test_full_size_properties_config2(torch_cuda):
     # frame independence: frames 5..8 alone
     as_sub, _, _ = ops.crf_forward(img[5:9].contiguous(), seg[5:9].contiguous(), cfg, check=True)
     assert rel_err(as_sub.cpu().numpy(), as1[5:9].cpu().numpy()) < 1e-5
+
+
+def test_cuda_graph_capture_and_replay(torch_cuda, oracle_mod):
+    """The device API never synchronises or allocates, so a whole fwd+bwd can be captured in a CUDA graph and
+    replayed on new data (table clearing, vertex counts and the loss ticket are all device-side)."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 4, 2, 64, 72
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    img = torch.zeros((n, 3, h, w), device="cuda")
+    seg = torch.zeros((n, k, h, w), device="cuda")
+    g_out = torch.tensor([0.5], device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        img.copy_(torch.from_numpy(synth.make_images(n, h, w, "noise", seed=1)))
+        seg.copy_(torch.from_numpy(synth.make_segs(n, k, h, w, seed=1)))
+        for _ in range(2):                              # warm-up on the capture stream (allocates the workspace)
+            as_t, loss, _ = ops.crf_forward(img, seg, cfg)
+            grad = ops.crf_backward(as_t, g_out, float(n))
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        as_t, loss, _ = ops.crf_forward(img, seg, cfg)
+        grad = ops.crf_backward(as_t, g_out, float(n))
+    for seed, kind in ((2, "natural"), (3, "noise")):
+        img_np = synth.make_images(n, h, w, kind, seed=seed)
+        seg_np = synth.make_segs(n, k, h, w, seed=seed)
+        img.copy_(torch.from_numpy(img_np))
+        seg.copy_(torch.from_numpy(seg_np))
+        graph.replay()
+        torch.cuda.synchronize()
+        want_loss, want_grad, want_as = oracle_mod.densecrf_loss_fwd_bwd(img_np, seg_np, 15.0, 100.0, 0.5,
+                                                                         oracle_mod.port_bilateralfilter_batch)
+        _assert_close(as_t.cpu().numpy(), want_as, f"graph AS {kind}")
+        _assert_close(grad.cpu().numpy(), want_grad, f"graph grad {kind}")
+        assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
 
 
 def test_temporal_max_bit_exact(torch_cuda):
