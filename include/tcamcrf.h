@@ -108,6 +108,17 @@ int tcamcrf_loss_forward_u8(const tcamcrf_config *cfg, const uint8_t *images_dev
 int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
                           float n_norm, void *cuda_stream);
 
+/* The same loss taken directly from LOGITS: segs = softmax(logits) over the K classes is
+ * formed on the fly inside the splat and slice kernels and never stored, and the backward pass goes through the
+ * softmax in the same kernel:  dz_k = p_k * (g_k - sum_j p_j g_j),  g = ((-2*grad_out)*AS)/n_norm.
+ * Replaces `F.softmax(fcams, dim=1)` + DenseCRFLoss in ConRanFieldTcams.forward (dlib/losses/tcam.py:109-115).
+ * images_dev is float32 (images_u8 = 0) or uint8 (images_u8 = 1).  K >= 2. */
+int tcamcrf_loss_forward_logits(const tcamcrf_config *cfg, const void *images_dev, int images_u8,
+                                const float *logits_dev, float *as_dev, float *loss_dev, int N, int K, int H, int W,
+                                float n_norm, void *workspace, size_t workspace_bytes, void *cuda_stream);
+int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
+                                 float *grad_logits_dev, int N, int K, int H, int W, float n_norm, void *cuda_stream);
+
 /* Reads the device status word of a workspace (synchronises the stream).  Returns 0 or TCAMCRF_DEV_* bits
  * in *dev_status; also writes the number of lattice vertices of the last chunk to *vertices (may be NULL). */
 int tcamcrf_workspace_status(void *workspace, void *cuda_stream, int *dev_status, int *vertices);

@@ -656,7 +656,8 @@ __device__ __forceinline__ void store_vec(float *addr, const float (&v)[V])
 }
 
 struct PixelParams {
-    const float *segs;      // [n][K][P]
+    const float *segs;      // [n][K][P]: class probabilities, or logits when `logits` is set
+    int logits;             // 1: segs holds logits; softmax over K is taken on the fly (never stored)
     float *as_out;          // [n][K][P]
     int *offset;            // [n][r][P]; entry index on entry to splat, dense id afterwards
     const float *bary;      // [n][r][P]
@@ -671,6 +672,26 @@ struct PixelParams {
     long long pool;
     float alpha;
 };
+
+// softmax over the K planes of one pixel without storing it: max and sum first, then
+// prob_k = exp(z_k - max) / sum, the order of operations of torch's softmax forward
+struct SoftmaxStat {
+    float zmax, sum;
+};
+__device__ __forceinline__ SoftmaxStat softmax_stat(const float *z, int K, int P)
+{
+    SoftmaxStat s;
+    s.zmax = -INFINITY;
+    for (int k = 0; k < K; k++) s.zmax = fmaxf(s.zmax, __ldg(z + (size_t)k * P));
+    s.sum = 0.f;
+    for (int k = 0; k < K; k++) s.sum += expf(__ldg(z + (size_t)k * P) - s.zmax);
+    return s;
+}
+__device__ __forceinline__ float seg_value(const float *z, int k, int P, int logits, const SoftmaxStat &st)
+{
+    const float v = __ldg(z + (size_t)k * P);
+    return logits ? __fdiv_rn(expf(v - st.zmax), st.sum) : v;
+}
 
 template <int D, int V>
 __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
@@ -705,10 +726,12 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
         any_run |= heads[r] != 0xffffffffu;
     }
     const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
+    SoftmaxStat sm = {0.f, 1.f};
+    if (p.logits && valid) sm = softmax_stat(seg, p.K, p.P);
     for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? __ldg(seg + (size_t)(k + e) * p.P) : 0.f;
+        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? seg_value(seg, k + e, p.P, p.logits, sm) : 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             float t[V];
@@ -814,6 +837,8 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
             w[r] = __fmul_rn(p.bary[base + (size_t)r * p.P], p.alpha);
         }
         const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
+        SoftmaxStat sm = {0.f, 1.f};
+        if (p.logits) sm = softmax_stat(seg, p.K, p.P);
         float *out = p.as_out + (size_t)n * p.K * p.P + pix;
         for (int k = 0; k < p.Kp; k += V) {
             float acc[V];
@@ -836,7 +861,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
                 if (k + e < p.K) {
                     const float o = poisoned ? __int_as_float(0x7fc00000) : acc[e];
                     out[(size_t)(k + e) * p.P] = o;
-                    dot = fmaf(__ldg(seg + (size_t)(k + e) * p.P), o, dot);
+                    dot = fmaf(seg_value(seg, k + e, p.P, p.logits, sm), o, dot);
                 }
             }
         }
@@ -907,6 +932,36 @@ __global__ void __launch_bounds__(kThreads) loss_backward_kernel(const float *__
         __stcs(g4 + i, g);
     }
     for (size_t i = n4 * 4 + tid; i < count; i += stride) grad[i] = __fdiv_rn(__fmul_rn(t, as[i]), n_norm);
+}
+
+// Backward through the CRF loss AND the softmax that produced its input, in one pass:
+//   g_k = ((-2*g) * AS_k) / n   (dense_crf_loss.py:73),   dz_k = p_k * (g_k - sum_j p_j g_j)
+// thread per pixel; logits / AS / grad planar [n][K][P]
+__global__ void __launch_bounds__(kThreads) loss_backward_logits_kernel(const float *__restrict__ as,
+                                                                        const float *__restrict__ logits,
+                                                                        const float *__restrict__ grad_out,
+                                                                        float *__restrict__ grad, int K, int P,
+                                                                        long long pixels, float n_norm)
+{
+    const float t = __fmul_rn(-2.0f, __ldg(grad_out));
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < pixels; i += stride) {
+        const long long n = i / P;
+        const size_t base = (size_t)n * K * P + (i - n * P);
+        const float *z = logits + base;
+        const float *a = as + base;
+        const SoftmaxStat sm = softmax_stat(z, K, P);
+        float inner = 0.f;
+        for (int k = 0; k < K; k++) {
+            const float pk = __fdiv_rn(expf(__ldg(z + (size_t)k * P) - sm.zmax), sm.sum);
+            inner = fmaf(pk, __fdiv_rn(__fmul_rn(t, __ldg(a + (size_t)k * P)), n_norm), inner);
+        }
+        for (int k = 0; k < K; k++) {
+            const float pk = __fdiv_rn(expf(__ldg(z + (size_t)k * P) - sm.zmax), sm.sum);
+            const float gk = __fdiv_rn(__fmul_rn(t, __ldg(a + (size_t)k * P)), n_norm);
+            grad[base + (size_t)k * P] = pk * (gk - inner);
+        }
+    }
 }
 
 // out[b][i] = max_t cams[b][t][i], NaN-propagating like torch.maximum
@@ -1016,7 +1071,7 @@ static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 template <int D>
 static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
                        float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
-                       cudaStream_t st)
+                       int logits, cudaStream_t st)
 {
     int *ctrl = (int *)(ws + pl.off_ctrl);
     Entry *table = (Entry *)(ws + pl.off_table);
@@ -1083,6 +1138,7 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
     const int V = (pl.Kp % 4 == 0) ? 4 : (pl.Kp % 2 == 0) ? 2 : 1;
     PixelParams pp;
     pp.segs = segs;
+    pp.logits = logits;
     pp.as_out = as_out;
     pp.offset = offset;
     pp.bary = bary;
@@ -1132,22 +1188,22 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
 
 static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
                      float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
-                     cudaStream_t st)
+                     int logits, cudaStream_t st)
 {
     switch (pl.D) {
-    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
-    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
-    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
-    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
-    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
-    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, st);
+    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
     }
     return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", pl.D);
 }
 
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
                       float *loss, int N, int K, int H, int W, float n_norm, void *workspace, size_t ws_bytes,
-                      cudaStream_t st)
+                      cudaStream_t st, int logits = 0)
 {
     if (!cfg || !images || !segs || !as_out || !workspace) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     Plan pl;
@@ -1167,7 +1223,7 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
         const char *img = (const char *)images + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem;
         const bool last = n0 + nc >= N;
         rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,
-                       loss != nullptr, last ? loss : nullptr, n_norm, st);
+                       loss != nullptr, last ? loss : nullptr, n_norm, logits, st);
         if (rc) return rc;
     }
     return TCAMCRF_OK;
@@ -1421,6 +1477,33 @@ int tcamcrf_loss_forward_u8(const tcamcrf_config *cfg, const uint8_t *images_dev
     if (!loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
     return run_filter(cfg, true, images_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
                       workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+int tcamcrf_loss_forward_logits(const tcamcrf_config *cfg, const void *images_dev, int images_u8,
+                                const float *logits_dev, float *as_dev, float *loss_dev, int N, int K, int H, int W,
+                                float n_norm, void *workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    if (!loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
+    if (K < 2) return fail(TCAMCRF_ERR_INVALID, "softmax needs at least two classes");
+    return run_filter(cfg, images_u8 != 0, images_dev, logits_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
+                      workspace_bytes, (cudaStream_t)cuda_stream, 1);
+}
+
+int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
+                                 float *grad_logits_dev, int N, int K, int H, int W, float n_norm, void *cuda_stream)
+{
+    if (!as_dev || !logits_dev || !grad_out_dev || !grad_logits_dev)
+        return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (N < 1 || K < 2 || H < 1 || W < 1) return fail(TCAMCRF_ERR_INVALID, "N,H,W must be positive and K >= 2");
+    const long long pixels = (long long)N * H * W;
+    long long blocks = (pixels + kThreads - 1) / kThreads;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    StageScope scope(kStBackward, 1, (cudaStream_t)cuda_stream);
+    loss_backward_logits_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)cuda_stream>>>(
+        as_dev, logits_dev, grad_out_dev, grad_logits_dev, K, H * W, pixels, n_norm);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
 }
 
 int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,

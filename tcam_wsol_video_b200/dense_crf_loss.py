@@ -18,7 +18,7 @@ from torch.autograd import Function
 
 from . import _lib, ops
 
-__all__ = ['DenseCRFLoss', 'DenseCRFLossFunction']
+__all__ = ['DenseCRFLoss', 'DenseCRFLossFunction', 'DenseCRFLossFromLogits', 'DenseCRFLossFromLogitsFunction']
 
 
 def _scale_images(images: torch.Tensor, scale_factor: float) -> torch.Tensor:
@@ -82,5 +82,50 @@ class DenseCRFLoss(nn.Module):
 
     def extra_repr(self):
         return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}'.format(
+            self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor
+        )
+
+
+class DenseCRFLossFromLogitsFunction(Function):
+    """``DenseCRFLossFunction`` applied to ``softmax(logits, dim=1)`` with the softmax (forward and backward)
+    fused into the CRF kernels -- the probabilities are never written to memory."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, images, logits, sigma_rgb, sigma_xy):
+        n = logits.shape[0]
+        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
+        logits = logits.detach().contiguous()
+        as_t, loss, _ = ops.crf_forward_logits(images, logits, cfg, n_norm=float(n))
+        ctx.AS = as_t
+        ctx.logits = logits
+        ctx.N = n
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, grad_output):
+        return None, ops.crf_backward_logits(ctx.AS, ctx.logits, grad_output, float(ctx.N)), None, None
+
+
+class DenseCRFLossFromLogits(nn.Module):
+    """Same value and gradient as ``DenseCRFLoss(...)(images, F.softmax(logits, dim=1))`` (what
+    ``ConRanFieldTcams.forward`` computes, dlib/losses/tcam.py:109-115) without materialising the softmax.
+    Only for ``scale_factor == 1`` (the reference rescales the probabilities, not the logits) and K >= 2."""
+
+    def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor=1.0):
+        super(DenseCRFLossFromLogits, self).__init__()
+        if scale_factor != 1.0:
+            raise ValueError('DenseCRFLossFromLogits supports scale_factor == 1 only')
+        self.weight = weight
+        self.sigma_rgb = sigma_rgb
+        self.sigma_xy = sigma_xy
+        self.scale_factor = scale_factor
+
+    def forward(self, images, logits):
+        return self.weight * DenseCRFLossFromLogitsFunction.apply(images, logits, self.sigma_rgb, self.sigma_xy)
+
+    def extra_repr(self):
+        return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}, fused_softmax=True'.format(
             self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor
         )

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .color_dense_crf_loss import ColorDenseCRFLoss
-from .dense_crf_loss import DenseCRFLoss
+from .dense_crf_loss import DenseCRFLoss, DenseCRFLossFromLogits
 
 __all__ = ['ElementaryLoss', 'ConRanFieldTcams', 'RgbJointConRanFieldTcams', 'SelfLearningTcams',
            'group_ordered_frames']
@@ -111,15 +111,24 @@ class SelfLearningTcams(ElementaryLoss):
 class ConRanFieldTcams(ElementaryLoss):
     """DenseCRF loss over the decoder's class probabilities (tcam.py:80-115)."""
 
-    def __init__(self, **kwargs):
+    def __init__(self, fuse_softmax: bool = False, **kwargs):
+        """``fuse_softmax=True`` (extension, off by default): the softmax over the classes and its backward run
+        inside the CRF kernels (``DenseCRFLossFromLogits``); needs scale_factor == 1 and more than one channel,
+        otherwise the unfused path is taken."""
         super(ConRanFieldTcams, self).__init__(**kwargs)
         self.loss = DenseCRFLoss(weight=self.lambda_, sigma_rgb=self.sigma_rgb, sigma_xy=self.sigma_xy,
                                  scale_factor=self.scale_factor).to(self._device)
+        self.loss_from_logits = None
+        if fuse_softmax and self.scale_factor == 1.0:
+            self.loss_from_logits = DenseCRFLossFromLogits(weight=self.lambda_, sigma_rgb=self.sigma_rgb,
+                                                           sigma_xy=self.sigma_xy, scale_factor=1.0).to(self._device)
 
     def forward(self, epoch=0, fcams=None, raw_img=None, **kwargs):
         super(ConRanFieldTcams, self).forward(epoch=epoch)
         if not self.is_on():
             return self._zero
+        if self.loss_from_logits is not None and fcams.shape[1] > 1:
+            return self.loss_from_logits(images=raw_img, logits=fcams)
         return self.loss(images=raw_img, segmentations=_probabilities(fcams))
 
 

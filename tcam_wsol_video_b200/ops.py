@@ -116,6 +116,59 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
     return as_out, loss, ws
 
 
+def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Config, n_norm: Optional[float] = None,
+                       check: Optional[bool] = None):
+    """Like crf_forward(want_loss=True) with segs = softmax(logits, dim=1) formed inside the kernels.
+    Returns (AS, loss [1], workspace)."""
+    lib = _lib.load()
+    _require_cuda(logits, "logits")
+    device = logits.device
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    logits = logits.contiguous()
+    n, k, h, w = logits.shape
+    if k < 2:
+        raise TcamCrfError("the fused softmax needs at least two classes")
+    images, u8 = _prep_images(images, device)
+    if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
+        raise TcamCrfError(f"images {tuple(images.shape)} do not match logits {tuple(logits.shape)}")
+    if images.shape[1] < cfg.channels:
+        raise TcamCrfError(f"images have {images.shape[1]} planes, config needs {cfg.channels}")
+    cfg.image_stride_planes = images.shape[1]
+    with torch.cuda.device(device):
+        nbytes = lib.tcamcrf_workspace_bytes(byref(cfg), n, k, h, w)
+        if nbytes == 0:
+            raise TcamCrfError("tcamcrf_workspace_bytes: " + _lib.last_error())
+        ws = _workspace(device, nbytes)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
+        as_out = torch.empty_like(logits)
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        rc = lib.tcamcrf_loss_forward_logits(byref(cfg), images.data_ptr(), 1 if u8 else 0, logits.data_ptr(),
+                                             as_out.data_ptr(), loss.data_ptr(), n, k, h, w,
+                                             float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
+                                             _stream_ptr(device))
+        _lib.check(rc, "tcamcrf_loss_forward_logits")
+        if STRICT if check is None else check:
+            _raise_on_status(ws if ws_ptr == ws.data_ptr() else ws[ws_ptr - ws.data_ptr():])
+    return as_out, loss, ws
+
+
+def crf_backward_logits(as_t: torch.Tensor, logits: torch.Tensor, grad_output: torch.Tensor, n_norm: float):
+    """Gradient w.r.t. the logits (CRF gradient chained through the softmax) in one kernel."""
+    lib = _lib.load()
+    _require_cuda(as_t, "AS")
+    n, k, h, w = as_t.shape
+    logits = logits.detach().float().contiguous()
+    g = grad_output.detach().reshape(-1)[:1].to(device=as_t.device, dtype=torch.float32).contiguous()
+    grad = torch.empty_like(as_t)
+    with torch.cuda.device(as_t.device):
+        _lib.check(lib.tcamcrf_loss_backward_logits(as_t.data_ptr(), logits.data_ptr(), g.data_ptr(), grad.data_ptr(),
+                                                    n, k, h, w, float(n_norm), _stream_ptr(as_t.device)),
+                   "tcamcrf_loss_backward_logits")
+    return grad
+
+
 def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float) -> torch.Tensor:
     """grad_seg = ((-2*g) * AS) / n_norm on the current stream (dlib/crf/dense_crf_loss.py:73)."""
     lib = _lib.load()
@@ -149,5 +202,5 @@ def temporal_cam_max(cams: torch.Tensor) -> torch.Tensor:
     return out
 
 
-__all__ = ["crf_forward", "crf_backward", "temporal_cam_max", "workspace_status", "release_workspaces",
+__all__ = ["crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

@@ -101,3 +101,29 @@ def test_self_learning_tcams_consumes_seeds(torch_cuda):
     assert torch.allclose(loss, want)
     loss.backward()
     assert int((seeds >= 0).sum()) <= b * 2 * 9 and fcams.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("k", [2, 10, 3])
+def test_fused_softmax_matches_unfused(torch_cuda, k):
+    """DenseCRFLossFromLogits == DenseCRFLoss o softmax, value and gradient w.r.t. the logits (rel 1e-4; the
+    only difference is exp() rounding), with float and uint8 images."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss, DenseCRFLossFromLogits
+    from tcam_wsol_video_b200.losses import ConRanFieldTcams
+    n, h, w = 3, 56, 64
+    raw = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=13))
+    logits = (3 * torch.randn((n, k, h, w), generator=torch.Generator().manual_seed(13))).cuda()
+    a = logits.clone().requires_grad_(True)
+    b = logits.clone().requires_grad_(True)
+    la = DenseCRFLoss(1e-6, 15., 100., 1.0)(images=raw, segmentations=torch.softmax(a, dim=1))
+    lb = DenseCRFLossFromLogits(1e-6, 15., 100., 1.0)(images=raw.to(torch.uint8).cuda(), logits=b)
+    la.backward()
+    lb.backward()
+    assert abs(la.item() - lb.item()) < REL_TOL * abs(la.item())
+    assert rel_err(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < REL_TOL
+    c = logits.clone().requires_grad_(True)
+    mod = ConRanFieldTcams(fuse_softmax=True, cuda_id=0, lambda_=1e-6, sigma_rgb=15., sigma_xy=100., scale_factor=1.0)
+    lc = mod(epoch=0, fcams=c, raw_img=raw)
+    lc.backward()
+    assert abs(la.item() - lc.item()) < REL_TOL * abs(la.item())
+    assert rel_err(c.grad.cpu().numpy(), a.grad.cpu().numpy()) < REL_TOL
