@@ -345,6 +345,45 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             extra[f"{kind}_k{k}"] = {"value": N * 30 / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "steps": 30}
             del img, seg
 
+        # BASELINE configs[2] without the backbone: per step, for 32 clips -- temporal max over the current + 4
+        # previous frames' CAMs fused with fg/bg seeding, CRF loss from logits (K=2, uint8 frames resident on the
+        # GPU, fused softmax) + cross-entropy on the seeds, backward to the logits.
+        try:
+            from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLossFromLogits
+            from tcam_wsol_video_b200.tcam_seeding import TCAMSeeder
+            low = torch.from_numpy(synth.make_low_res_cams(N, 5, 28, 28, seed=3)).squeeze(2)
+            cams = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False).to(dev)
+            roi = (cams.amax(dim=1, keepdim=True) >= 0.5).long()
+            img8 = torch.from_numpy(synth.make_images(N, H, W, "natural", seed=3).astype(np.uint8)).to(dev)
+            logits = torch.randn((N, 2, H, W), device=dev, requires_grad=True)
+            seeder = TCAMSeeder(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11,
+                                fg_erode_iter=0, ksz=3, support_background=True, multi_label_flag=False,
+                                seg_ignore_idx=-255, cuda_id=local_rank, roi_method="roi_all", p_min_area_roi=0.05,
+                                use_roi=True, rng_parity=False)
+            crf2 = DenseCRFLossFromLogits(2e-9, SIGMA_RGB, SIGMA_XY, 1.0)
+
+            def tcam_step():
+                logits.grad = None
+                seeds, _ = seeder.forward_stack(cams, roi)
+                loss = crf2(images=img8, logits=logits) + torch.nn.functional.cross_entropy(logits, seeds,
+                                                                                             ignore_index=-255)
+                loss.backward()
+
+            for _ in range(5):
+                tcam_step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(30):
+                tcam_step()
+            e1.record()
+            torch.cuda.synchronize()
+            extra["tcam_seed_crf_step_natural_k2"] = {
+                "value": N * 30 / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "steps": 30,
+                "what": "temporal max (T=5) + seeding + CRF-from-logits + CE on seeds, fwd+bwd, no backbone"}
+        except Exception as exc:  # context only; never fail the headline line
+            extra["tcam_seed_crf_step_natural_k2"] = {"error": repr(exc)[:200]}
+
     if rank != 0:
         return
 

@@ -687,13 +687,14 @@ __device__ __forceinline__ SoftmaxStat softmax_stat(const float *z, int K, int P
     for (int k = 0; k < K; k++) s.sum += expf(__ldg(z + (size_t)k * P) - s.zmax);
     return s;
 }
-__device__ __forceinline__ float seg_value(const float *z, int k, int P, int logits, const SoftmaxStat &st)
+template <bool L>
+__device__ __forceinline__ float seg_value(const float *z, int k, int P, const SoftmaxStat &st)
 {
     const float v = __ldg(z + (size_t)k * P);
-    return logits ? __fdiv_rn(expf(v - st.zmax), st.sum) : v;
+    return L ? __fdiv_rn(expf(v - st.zmax), st.sum) : v;
 }
 
-template <int D, int V>
+template <int D, int V, bool L>
 __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
 {
     const int n = blockIdx.y;
@@ -727,11 +728,11 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     }
     const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
     SoftmaxStat sm = {0.f, 1.f};
-    if (p.logits && valid) sm = softmax_stat(seg, p.K, p.P);
+    if (L && valid) sm = softmax_stat(seg, p.K, p.P);
     for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? seg_value(seg, k + e, p.P, p.logits, sm) : 0.f;
+        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? seg_value<L>(seg, k + e, p.P, sm) : 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             float t[V];
@@ -818,7 +819,7 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int 
     }
 }
 
-template <int D, int V>
+template <int D, int V, bool L>
 __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
 {
     __shared__ float s_red[kThreads / 32];
@@ -838,7 +839,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
         }
         const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
         SoftmaxStat sm = {0.f, 1.f};
-        if (p.logits) sm = softmax_stat(seg, p.K, p.P);
+        if (L) sm = softmax_stat(seg, p.K, p.P);
         float *out = p.as_out + (size_t)n * p.K * p.P + pix;
         for (int k = 0; k < p.Kp; k += V) {
             float acc[V];
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
                 if (k + e < p.K) {
                     const float o = poisoned ? __int_as_float(0x7fc00000) : acc[e];
                     out[(size_t)(k + e) * p.P] = o;
-                    dot = fmaf(seg_value(seg, k + e, p.P, p.logits, sm), o, dot);
+                    dot = fmaf(seg_value<L>(seg, k + e, p.P, sm), o, dot);
                 }
             }
         }
@@ -1038,24 +1039,31 @@ static void launch_build(const BuildParams &bp, dim3 grid, cudaStream_t st)
     build_kernel<D, ImgT><<<grid, kThreads, 0, st>>>(bp);
 }
 
+template <int D, int V>
+static void launch_pixel_v(bool splat, const PixelParams &pp, dim3 grid, cudaStream_t st)
+{
+    if (splat) {
+        if (pp.logits)
+            splat_kernel<D, V, true><<<grid, kThreads, 0, st>>>(pp);
+        else
+            splat_kernel<D, V, false><<<grid, kThreads, 0, st>>>(pp);
+    } else {
+        if (pp.logits)
+            slice_kernel<D, V, true><<<grid, kThreads, 0, st>>>(pp);
+        else
+            slice_kernel<D, V, false><<<grid, kThreads, 0, st>>>(pp);
+    }
+}
+
 template <int D>
 static void launch_pixel(bool splat, int V, const PixelParams &pp, dim3 grid, cudaStream_t st)
 {
-    if (splat) {
-        if (V == 4)
-            splat_kernel<D, 4><<<grid, kThreads, 0, st>>>(pp);
-        else if (V == 2)
-            splat_kernel<D, 2><<<grid, kThreads, 0, st>>>(pp);
-        else
-            splat_kernel<D, 1><<<grid, kThreads, 0, st>>>(pp);
-    } else {
-        if (V == 4)
-            slice_kernel<D, 4><<<grid, kThreads, 0, st>>>(pp);
-        else if (V == 2)
-            slice_kernel<D, 2><<<grid, kThreads, 0, st>>>(pp);
-        else
-            slice_kernel<D, 1><<<grid, kThreads, 0, st>>>(pp);
-    }
+    if (V == 4)
+        launch_pixel_v<D, 4>(splat, pp, grid, st);
+    else if (V == 2)
+        launch_pixel_v<D, 2>(splat, pp, grid, st);
+    else
+        launch_pixel_v<D, 1>(splat, pp, grid, st);
 }
 
 static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
