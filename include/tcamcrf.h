@@ -179,6 +179,11 @@ int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const
 int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
                      int64_t *out_dev, void *cuda_stream);
 
+/* ROI of every CAM of a batch by Otsu's threshold: roi = (cam*255 >= otsu(floor(cam*255))), 1/0 as int64, the
+ * 'roi_all' branch of GetRoiSingleCam (dlib/cams/tcam_seeding.py:316-345,419-430; scikit-image threshold_otsu
+ * on a 256-bin np.histogram, float32 edges).  cams_dev [B,HW] float32, roi_dev [B,HW], thresh_dev [B] or NULL. */
+int tcam_otsu_roi(const float *cams_dev, int64_t *roi_dev, float *thresh_dev, int B, int HW, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

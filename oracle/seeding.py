@@ -120,3 +120,40 @@ def tcam_seeder_forward(x, roi=None, *, seed_tech, min_, max_, min_p, max_p, ksz
     out[all_fg == 1] = 1
     out[all_bg == 1] = 0
     return out.detach()
+
+
+# --------------------------------------------------------------------------------------------------
+# ROI by Otsu (numpy, like the reference runs it on the CPU)
+# --------------------------------------------------------------------------------------------------
+def threshold_otsu_skimage(image, nbins=256):
+    """scikit-image 0.17.2 ``skimage.filters.threshold_otsu`` restated (third-party, requirements.txt:83;
+    not installed here -> parity UNPINNED against the real package).  ``histogram(image.ravel(), nbins,
+    source_range='image')`` is ``np.histogram(image, bins=nbins)`` plus bin centres for float images."""
+    import numpy as np
+    first_pixel = image.ravel()[0]
+    if np.all(image == first_pixel):
+        return first_pixel
+    hist, bin_edges = np.histogram(image.ravel(), bins=nbins, range=None)
+    bin_centers = (bin_edges[:-1] + bin_edges[1:]) / 2.
+    hist = hist.astype(float)
+    weight1 = np.cumsum(hist)
+    weight2 = np.cumsum(hist[::-1])[::-1]
+    mean1 = np.cumsum(hist * bin_centers) / weight1
+    mean2 = (np.cumsum((hist * bin_centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    idx = np.argmax(variance12)
+    return bin_centers[:-1][idx]
+
+
+def roi_all_single_cam(cam):
+    """GetRoiSingleCam(roi_method='roi_all').__call__ + get_thresh (dlib/cams/tcam_seeding.py:325-345,419-430)
+    for one CAM given as a float32 numpy array [h,w]; returns (roi int64 [h,w], threshold on the 0..255 scale)."""
+    import numpy as np
+    _cam = np.asarray(cam, dtype=np.float32)
+    cam_ = np.floor(_cam * 255.)
+    if cam_.min() == cam_.max():
+        th = 0.
+    else:
+        th = threshold_otsu_skimage(cam_)
+    blobs = (_cam * 255. >= th).astype(int)
+    return blobs.astype(np.int64), float(th)

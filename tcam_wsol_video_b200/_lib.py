@@ -113,6 +113,7 @@ SIGNATURES = {
     "tcam_temporal_max": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tcam_seed_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "tcam_otsu_roi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tcam_seed_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
 }
 

@@ -280,4 +280,100 @@ __global__ void __launch_bounds__(256) seed_labels_kernel(const int *__restrict_
     }
 }
 
+// ROI of a CAM by Otsu's threshold, one thread block per sample.  Restates, on the GPU,
+//   GetRoiSingleCam.get_thresh + __call__ with roi_method == 'roi_all' (dlib/cams/tcam_seeding.py:337-345,419-430):
+//     cam_ = floor(cam * 255.);  th = 0 if flat else skimage.filters.threshold_otsu(cam_);  roi = cam*255. >= th
+//   skimage 0.17.2 threshold_otsu (third-party, requirements.txt:83): 256-bin np.histogram over [min, max],
+//     bin centres, between-class variance in float64, threshold = centre of the arg-max bin.
+// np.histogram's float32 arithmetic is reproduced step by step: edges[i] = fl(fl(i*step) + first) (np.linspace),
+// index = trunc(((v - first) / (last - first)) * 256) with the +-1 corrections against the edges.
+__global__ void __launch_bounds__(kSeedThreads) otsu_roi_kernel(const float *__restrict__ cams,
+                                                                long long *__restrict__ roi,
+                                                                float *__restrict__ thresh_out, int HW)
+{
+    __shared__ float s_edge[257];
+    __shared__ int s_hist[256];
+    __shared__ float s_red[2][32];
+    __shared__ float s_th;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float *cam = cams + (size_t)b * HW;
+
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        const float v = floorf(__fmul_rn(__ldg(cam + i), 255.0f));
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = lo;
+        s_red[1][tid >> 5] = hi;
+    }
+    __syncthreads();
+    lo = s_red[0][0];
+    hi = s_red[1][0];
+    for (int w = 1; w < kSeedThreads / 32; w++) {
+        lo = fminf(lo, s_red[0][w]);
+        hi = fmaxf(hi, s_red[1][w]);
+    }
+    const bool flat = !(lo < hi);
+    if (!flat) {
+        const float step = __fdiv_rn(__fsub_rn(hi, lo), 256.0f);
+        for (int i = tid; i < 257; i += kSeedThreads)
+            s_edge[i] = i == 256 ? hi : __fadd_rn(__fmul_rn((float)i, step), lo);
+        for (int i = tid; i < 256; i += kSeedThreads) s_hist[i] = 0;
+        __syncthreads();
+        const float denom = __fsub_rn(hi, lo);
+        for (int i = tid; i < HW; i += kSeedThreads) {
+            const float v = floorf(__fmul_rn(__ldg(cam + i), 255.0f));
+            int idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(v, lo), denom), 256.0f);
+            if (idx == 256) idx = 255;
+            if (v < s_edge[idx]) idx -= 1;
+            if (v >= s_edge[idx + 1] && idx != 255) idx += 1;
+            atomicAdd(&s_hist[idx], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // sequential float64 cumulative sums, like np.cumsum
+            double w2_after[257], m2_after[257];   // suffix sums from bin i on
+            double run_w = 0.0, run_m = 0.0;
+            w2_after[256] = 0.0;
+            m2_after[256] = 0.0;
+            for (int i = 255; i >= 0; i--) {
+                const float centre = __fdiv_rn(__fadd_rn(s_edge[i], s_edge[i + 1]), 2.0f);
+                run_w += (double)s_hist[i];
+                run_m += (double)s_hist[i] * (double)centre;
+                w2_after[i] = run_w;
+                m2_after[i] = run_m / run_w;          // mean2[i]
+            }
+            double w1 = 0.0, m1 = 0.0, best = -1.0;
+            int best_i = 0;
+            for (int i = 0; i < 255; i++) {
+                const float centre = __fdiv_rn(__fadd_rn(s_edge[i], s_edge[i + 1]), 2.0f);
+                w1 += (double)s_hist[i];
+                m1 += (double)s_hist[i] * (double)centre;
+                const double mean1 = m1 / w1;
+                const double d = mean1 - m2_after[i + 1];
+                const double var = (w1 * w2_after[i + 1]) * (d * d);
+                if (var > best) {                     // np.argmax: first maximum
+                    best = var;
+                    best_i = i;
+                }
+            }
+            s_th = __fdiv_rn(__fadd_rn(s_edge[best_i], s_edge[best_i + 1]), 2.0f);
+        }
+    } else if (tid == 0) {
+        s_th = 0.0f;
+    }
+    __syncthreads();
+    const float th = s_th;
+    if (tid == 0 && thresh_out) thresh_out[b] = th;
+    long long *out = roi + (size_t)b * HW;
+    for (int i = tid; i < HW; i += kSeedThreads) out[i] = __fmul_rn(__ldg(cam + i), 255.0f) >= th ? 1 : 0;
+}
+
 }  // namespace tcamcrf

@@ -1745,6 +1745,19 @@ int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz,
     return TCAMCRF_OK;
 }
 
+int tcam_otsu_roi(const float *cams_dev, int64_t *roi_dev, float *thresh_dev, int B, int HW, void *cuda_stream)
+{
+    if (!cams_dev || !roi_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || HW < 1) return fail(TCAMCRF_ERR_INVALID, "B,HW must be positive");
+    {
+        StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+        otsu_roi_kernel<<<B, kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(
+            cams_dev, reinterpret_cast<long long *>(roi_dev), thresh_dev, HW);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
 int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream)
 {
     if (!cams_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");

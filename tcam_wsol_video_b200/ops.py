@@ -202,5 +202,22 @@ def temporal_cam_max(cams: torch.Tensor) -> torch.Tensor:
     return out
 
 
-__all__ = ["crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
+def otsu_roi(cams: torch.Tensor):
+    """ROI masks by Otsu's threshold for a batch of CAMs [B,1,H,W] or [B,H,W] (float32, CUDA).
+    Returns (roi long, same shape as cams; thresholds float32 [B] on the 0..255 scale).
+    GPU version of GetRoiSingleCam with roi_method='roi_all' (dlib/cams/tcam_seeding.py:316-345)."""
+    lib = _lib.load()
+    _require_cuda(cams, "cams")
+    x = cams.detach().float().contiguous()
+    b = x.shape[0]
+    hw = x[0].numel()
+    roi = torch.empty(x.shape, dtype=torch.long, device=x.device)
+    th = torch.empty(b, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tcam_otsu_roi(x.data_ptr(), roi.data_ptr(), th.data_ptr(), b, hw, _stream_ptr(x.device)),
+                   "tcam_otsu_roi")
+    return roi, th
+
+
+__all__ = ["otsu_roi", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

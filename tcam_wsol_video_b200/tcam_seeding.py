@@ -13,8 +13,9 @@ current torch CUDA generator with the same sizes and in the same order as the re
 (sample 0 fg, sample 0 bg, sample 1 fg, ...), so for the same seed the seeds are bit-identical to the
 reference's.  ``rng_parity=False`` draws everything in one call (same distribution, different stream).
 
-Not supported (raises): ``use_roi=True`` with ``roi=None`` -- the reference then computes the ROI on the CPU
-with scikit-image's Otsu (tcam_seeding.py:476-479), which is outside this path.
+``use_roi=True`` with ``roi=None``: the reference computes the ROI on the CPU with scikit-image's Otsu, one
+sample at a time (tcam_seeding.py:476-479); here ``roi_method='roi_all'`` runs as one kernel for the batch
+(``tcam_otsu_roi``).  The connected-component ROI modes still raise.
 """
 from __future__ import annotations
 
@@ -200,8 +201,11 @@ class TCAMSeeder(nn.Module):
         _roi = None
         if self.use_roi:
             if roi is None:
-                raise NotImplementedError('use_roi=True needs the roi tensor (the reference falls back to a CPU '
-                                          'scikit-image Otsu, which is outside this path)')
+                # the reference falls back to GetRoiSingleCam on the CPU here (tcam_seeding.py:476-479)
+                if self.roi_method != ROI_ALL:
+                    raise NotImplementedError(f'roi=None with roi_method={self.roi_method!r}: only {ROI_ALL!r} has a '
+                                              'GPU implementation (the others need connected components on the CPU)')
+                roi, _ = ops.otsu_roi(x)
             _roi = self._erode(roi.to(x.device)).long().contiguous()
         return x.detach().float().contiguous(), _roi
 

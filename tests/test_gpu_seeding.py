@@ -121,9 +121,51 @@ def test_seeder_api_surface(torch_cuda):
     out = mod.use_all_roi(cam, roi)
     assert torch.equal(out == 1, roi.squeeze(1) == 1) and ((out == 1) | (out == -255)).all()
     with pytest.raises(NotImplementedError):
-        mod(x=cam, roi=None)
+        _seeder(roi_method="largest")(x=cam, roi=None)
     # erosion of the roi before sampling (fg_erode_iter > 0) keeps seeds inside the eroded region
     mod = _seeder(fg_erode_k=5, fg_erode_iter=1, ksz=1, max_=8)
     seeds = mod(x=cam, roi=roi)
     eroded = mod._erode(roi).squeeze(1)
     assert ((seeds == 1) <= (eroded == 1)).all()
+
+
+@pytest.mark.parametrize("kind", ["bilinear", "uniform", "quantised", "flat"])
+def test_otsu_roi_matches_numpy_restatement(torch_cuda, kind):
+    """tcam_otsu_roi vs the reference's CPU recipe (np.histogram + scikit-image's Otsu restated): same
+    threshold bit for bit and the same mask, on CAM-like, uniform, heavily tied and flat inputs."""
+    torch = torch_cuda
+    from oracle import seeding as ref
+    from tcam_wsol_video_b200 import ops
+    b, h, w = 6, 224, 224
+    g = torch.Generator().manual_seed(17)
+    if kind == "bilinear":
+        cam = torch.nn.functional.interpolate(torch.rand((b, 1, 28, 28), generator=g), size=(h, w), mode="bilinear",
+                                              align_corners=False)
+    elif kind == "uniform":
+        cam = torch.rand((b, 1, h, w), generator=g)
+    elif kind == "quantised":
+        cam = torch.randint(0, 7, (b, 1, h, w), generator=g).float() / 9 + 0.01
+    else:
+        cam = torch.full((b, 1, h, w), 0.3)
+        cam[1] = torch.rand((1, h, w), generator=g) * 0.5       # one non-flat sample among flat ones
+    roi, th = ops.otsu_roi(cam.cuda())
+    assert roi.shape == cam.shape and roi.dtype == torch.long
+    for i in range(b):
+        want_roi, want_th = ref.roi_all_single_cam(cam[i, 0].numpy())
+        assert th[i].item() == np.float32(want_th), (i, th[i].item(), want_th)
+        assert np.array_equal(roi[i, 0].cpu().numpy(), want_roi)
+
+
+def test_seeder_computes_roi_when_none_is_given(torch_cuda):
+    """use_roi=True, roi=None: the reference calls GetRoiSingleCam per sample on the CPU; here one kernel."""
+    torch = torch_cuda
+    from oracle import seeding as ref
+    cam, _ = _make(torch, 4, 96, 80, seed=9)
+    mod = _seeder()
+    torch.manual_seed(5)
+    got = mod(x=cam, roi=None)
+    roi = torch.stack([torch.from_numpy(ref.roi_all_single_cam(cam[i, 0].cpu().numpy())[0]) for i in range(4)])
+    torch.manual_seed(5)
+    want = ref.tcam_seeder_forward(cam, roi.unsqueeze(1).cuda(), seed_tech=mod.seed_tech, min_=1, max_=1, min_p=0.1,
+                                   max_p=0.6, ksz=3, ignore_idx=-255, use_roi=True)
+    assert torch.equal(got, want)
