@@ -94,6 +94,14 @@ int tcamcrf_filter(const tcamcrf_config *cfg, const float *images_dev, const flo
 int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev, float *as_dev,
                       int N, int K, int H, int W, void *workspace, size_t workspace_bytes, void *cuda_stream);
 
+/* A^T * segs: the same filter with the blur axes applied in the opposite order (d..0).  Each single-axis blur is
+ * symmetric and slice is the transpose of splat, so this is exactly the transposed operator.  Not used by the
+ * reference (its backward is -2*g*AS/N, dense_crf_loss.py:73, which treats A as symmetric); it backs the opt-in
+ * exact gradient -(g/N)*(A + A^T)*segs of DenseCRFLoss(exact_gradient=True). */
+int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev, int images_u8, const float *segs_dev,
+                               float *ats_dev, int N, int K, int H, int W, void *workspace, size_t workspace_bytes,
+                               void *cuda_stream);
+
 /* Forward of the DenseCRF loss: as_dev as above and loss_dev[0] = -sum(segs*AS)/n_norm
  * (dlib/crf/dense_crf_loss.py:56-66).  n_norm is the reference's N (the local batch size). */
 int tcamcrf_loss_forward(const tcamcrf_config *cfg, const float *images_dev, const float *segs_dev, float *as_dev,

@@ -94,6 +94,7 @@ SIGNATURES = {
     "tcamcrf_device_count": (c_int, []),
     "tcamcrf_workspace_bytes": (c_size_t, [_cfgp, c_int, c_int, c_int, c_int]),
     "tcamcrf_filter": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "tcamcrf_filter_transposed": (c_int, [_cfgp, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_filter_u8": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_loss_forward": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_loss_forward_u8": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),

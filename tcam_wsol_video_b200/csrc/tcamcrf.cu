@@ -131,6 +131,8 @@ struct StageScope {
 // workspace layout
 // ---------------------------------------------------------------------------
 constexpr int kThreads = 256;
+constexpr int kFlagLogits = 1;        // segs holds logits, softmax on the fly
+constexpr int kFlagReverseBlur = 2;   // blur axes d..0: the transposed filter
 
 
 
@@ -1079,8 +1081,9 @@ static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 template <int D>
 static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
                        float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
-                       int logits, cudaStream_t st)
+                       int flags, cudaStream_t st)
 {
+    const int logits = flags & kFlagLogits;
     int *ctrl = (int *)(ws + pl.off_ctrl);
     Entry *table = (Entry *)(ws + pl.off_table);
     int *offset = (int *)(ws + pl.off_offset);
@@ -1174,7 +1177,9 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
             BlurParams bl;
             bl.src = src;
             bl.dst = dst;
-            bl.nbr = nbr + (size_t)j * pl.pool;
+            // axes 0..d like the reference (permutohedral.cpp:537); d..0 gives the transposed filter, because
+            // every single-axis blur is symmetric
+            bl.nbr = nbr + (size_t)((flags & kFlagReverseBlur) ? D - j : j) * pl.pool;
             bl.ctrl = ctrl;
             bl.Kp = pl.Kp;
             bl.stride = pl.stride;
@@ -1196,22 +1201,22 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
 
 static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
                      float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
-                     int logits, cudaStream_t st)
+                     int flags, cudaStream_t st)
 {
     switch (pl.D) {
-    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
-    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
-    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
-    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
-    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
-    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, logits, st);
+    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
+    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
+    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
+    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
+    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
+    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
     }
     return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", pl.D);
 }
 
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
                       float *loss, int N, int K, int H, int W, float n_norm, void *workspace, size_t ws_bytes,
-                      cudaStream_t st, int logits = 0)
+                      cudaStream_t st, int flags = 0)
 {
     if (!cfg || !images || !segs || !as_out || !workspace) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     Plan pl;
@@ -1231,7 +1236,7 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
         const char *img = (const char *)images + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem;
         const bool last = n0 + nc >= N;
         rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,
-                       loss != nullptr, last ? loss : nullptr, n_norm, logits, st);
+                       loss != nullptr, last ? loss : nullptr, n_norm, flags, st);
         if (rc) return rc;
     }
     return TCAMCRF_OK;
@@ -1462,6 +1467,14 @@ int tcamcrf_filter(const tcamcrf_config *cfg, const float *images_dev, const flo
                       workspace_bytes, (cudaStream_t)cuda_stream);
 }
 
+int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev, int images_u8, const float *segs_dev,
+                               float *ats_dev, int N, int K, int H, int W, void *workspace, size_t workspace_bytes,
+                               void *cuda_stream)
+{
+    return run_filter(cfg, images_u8 != 0, images_dev, segs_dev, ats_dev, nullptr, N, K, H, W, 1.f, workspace,
+                      workspace_bytes, (cudaStream_t)cuda_stream, kFlagReverseBlur);
+}
+
 int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev, float *as_dev,
                       int N, int K, int H, int W, void *workspace, size_t workspace_bytes, void *cuda_stream)
 {
@@ -1494,7 +1507,7 @@ int tcamcrf_loss_forward_logits(const tcamcrf_config *cfg, const void *images_de
     if (!loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
     if (K < 2) return fail(TCAMCRF_ERR_INVALID, "softmax needs at least two classes");
     return run_filter(cfg, images_u8 != 0, images_dev, logits_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
-                      workspace_bytes, (cudaStream_t)cuda_stream, 1);
+                      workspace_bytes, (cudaStream_t)cuda_stream, kFlagLogits);
 }
 
 int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, const float *grad_out_dev,

@@ -39,34 +39,49 @@ class DenseCRFLossFunction(Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type='cuda')
-    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy):
+    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False):
         n = segmentations.shape[0]
         cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
         as_t, loss, _ = ops.crf_forward(images, segmentations.detach(), cfg, want_loss=True, n_norm=float(n))
         ctx.AS = as_t
         ctx.N = n
+        ctx.exact = bool(exact_gradient)
+        if ctx.exact:   # the transposed filter needs the lattice again: keep what rebuilds it
+            ctx.images = images
+            ctx.segs = segmentations.detach()
+            ctx.sigmas = (sigma_rgb, sigma_xy)
         return loss
 
     @staticmethod
     @torch.amp.custom_bwd(device_type='cuda')
     def backward(ctx, grad_output):
-        grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N))
-        return None, grad_segmentation, None, None
+        if ctx.exact:
+            # d/dS [-S.(A S)/N] = -(A + A^T) S / N.  The reference uses -2 A S / N (dense_crf_loss.py:73), which is
+            # exact only for a symmetric A; the blur axes are applied in a fixed order, so A != A^T in general.
+            cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, ctx.sigmas[0], ctx.sigmas[1])
+            ats = ops.crf_filter_transposed(ctx.images, ctx.segs, cfg)
+            grad_segmentation = ops.crf_backward((ctx.AS + ats) * 0.5, grad_output, float(ctx.N))
+        else:
+            grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N))
+        return None, grad_segmentation, None, None, None
 
 
 class DenseCRFLoss(nn.Module):
-    def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor):
+    def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor, exact_gradient=False):
         """
         :param weight: float. lambda of the CRF loss.
         :param sigma_rgb: float. colour bandwidth of the bilateral kernel.
         :param sigma_xy: float. spatial bandwidth of the bilateral kernel.
         :param scale_factor: float. images and segmentations are rescaled by it first.
+        :param exact_gradient: bool, extension, OFF by default (reference behaviour: grad = -2*g*AS/N).  When on,
+            the backward pass runs the transposed filter and returns the true gradient -g*(A + A^T)S/N.
         """
         super(DenseCRFLoss, self).__init__()
         self.weight = weight
         self.sigma_rgb = sigma_rgb
         self.sigma_xy = sigma_xy
         self.scale_factor = scale_factor
+        self.exact_gradient = exact_gradient
 
     def forward(self, images, segmentations):
         """
@@ -77,7 +92,7 @@ class DenseCRFLoss(nn.Module):
         scaled_images = _scale_images(images, self.scale_factor)
         scaled_segs = _scale_segs(segmentations, self.scale_factor)
         val = self.weight * DenseCRFLossFunction.apply(
-            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor)
+            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient)
         return val
 
     def extra_repr(self):

@@ -116,6 +116,29 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
     return as_out, loss, ws
 
 
+def crf_filter_transposed(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config) -> torch.Tensor:
+    """A^T segs (blur axes in reverse order) on the current stream; see tcamcrf_filter_transposed."""
+    lib = _lib.load()
+    _require_cuda(segs, "segmentations")
+    device = segs.device
+    segs = segs.detach().float().contiguous()
+    n, k, h, w = segs.shape
+    images, u8 = _prep_images(images, device)
+    cfg.image_stride_planes = images.shape[1]
+    with torch.cuda.device(device):
+        nbytes = lib.tcamcrf_workspace_bytes(byref(cfg), n, k, h, w)
+        if nbytes == 0:
+            raise TcamCrfError("tcamcrf_workspace_bytes: " + _lib.last_error())
+        ws = _workspace(device, nbytes)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        out = torch.empty_like(segs)
+        _lib.check(lib.tcamcrf_filter_transposed(byref(cfg), images.data_ptr(), 1 if u8 else 0, segs.data_ptr(),
+                                                 out.data_ptr(), n, k, h, w, ws_ptr,
+                                                 ws.numel() - (ws_ptr - ws.data_ptr()), _stream_ptr(device)),
+                   "tcamcrf_filter_transposed")
+    return out
+
+
 def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Config, n_norm: Optional[float] = None,
                        check: Optional[bool] = None):
     """Like crf_forward(want_loss=True) with segs = softmax(logits, dim=1) formed inside the kernels.
@@ -219,5 +242,5 @@ def otsu_roi(cams: torch.Tensor):
     return roi, th
 
 
-__all__ = ["otsu_roi", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
+__all__ = ["otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

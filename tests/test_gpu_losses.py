@@ -127,3 +127,41 @@ def test_fused_softmax_matches_unfused(torch_cuda, k):
     lc.backward()
     assert abs(la.item() - lc.item()) < REL_TOL * abs(la.item())
     assert rel_err(c.grad.cpu().numpy(), a.grad.cpu().numpy()) < REL_TOL
+
+
+def test_exact_gradient_option(torch_cuda, oracle_mod):
+    """Opt-in exact gradient: -(A + A^T) S g / N.  Checked three ways: (1) the transposed filter really is the
+    transpose, <V, A S> == <A^T V, S>; (2) the directional derivative of the (quadratic) loss along a random V
+    equals <grad_exact, V>; (3) the default stays the reference's -2 g A S / N."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import _lib, ops
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    n, k, h, w = 2, 3, 40, 48
+    raw = torch.from_numpy(synth.make_images(n, h, w, "noise", seed=21))
+    gen = torch.Generator().manual_seed(21)
+    s = torch.softmax(torch.randn((n, k, h, w), generator=gen), dim=1).cuda()
+    v = torch.randn((n, k, h, w), generator=gen).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    a_s, _, _ = ops.crf_forward(raw, s, cfg, want_loss=False)
+    at_v = ops.crf_filter_transposed(raw, v, cfg)
+    lhs = (v.double() * a_s.double()).sum().item()
+    rhs = (at_v.double() * s.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs)
+    # the filter is NOT symmetric: A^T V differs from A V
+    a_v, _, _ = ops.crf_forward(raw, v, cfg, want_loss=False)
+    assert rel_err(at_v.cpu().numpy(), a_v.cpu().numpy()) > 1e-4
+
+    weight = 1e-3
+    s1 = s.clone().requires_grad_(True)
+    DenseCRFLoss(weight, 15.0, 100.0, 1.0, exact_gradient=True)(images=raw, segmentations=s1).backward()
+    # L(S + eV) = L(S) + e * <grad, V> + e^2 * L_2: read the linear term off two evaluations
+    def loss_at(t):
+        return DenseCRFLoss(weight, 15.0, 100.0, 1.0)(images=raw, segmentations=(s + t * v)).double().item()
+    eps = 1.0
+    directional = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
+    got = (s1.grad.double() * v.double()).sum().item()
+    assert abs(got - directional) < 2e-4 * abs(directional)
+    s2 = s.clone().requires_grad_(True)
+    DenseCRFLoss(weight, 15.0, 100.0, 1.0)(images=raw, segmentations=s2).backward()
+    want = (-2.0 * weight * a_s / n)
+    assert rel_err(s2.grad.cpu().numpy(), want.cpu().numpy()) < 1e-6
