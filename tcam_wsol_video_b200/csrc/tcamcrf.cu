@@ -198,6 +198,10 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     pl.W = W;
     pl.P = H * W;
     int chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 64;
+    if (const char *env = getenv("TCAMCRF_CHUNK")) {   // tuning sweeps only (tools/sweep.sh)
+        const int v = atoi(env);
+        if (v > 0) chunk = v;
+    }
     if (chunk > 256) chunk = 256;  // kMaxChunk: the vertex kernels keep a per-frame prefix sum in shared memory
     pl.chunk = chunk < N ? chunk : N;
     // every pixel (+ the ghost pixel) contributes at most d+1 distinct vertices
@@ -315,9 +319,6 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
 // 4 blocks 0.221 / 0.119, 5 blocks 0.214 / 0.109, 6 blocks 0.218 / 0.107, 8 blocks 0.235 / 0.107.
 #ifndef TCAMCRF_BUILD_MINBLOCKS
 #define TCAMCRF_BUILD_MINBLOCKS 5
-#endif
-#ifndef TCAMCRF_BLUR_U
-#define TCAMCRF_BLUR_U 1
 #endif
 template <int D, typename ImgT>
 __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kernel(const BuildParams p)
@@ -495,6 +496,9 @@ struct VertexParams {
     long long pool;
     int Kp;
     int sig;
+    int frame0;             // first frame of the chunk this launch works on (0 unless the host path runs the
+                            // value stages group by group on a lattice built for the whole batch)
+    int zero_values, preset_links;   // what vertex_init_kernel clears
 };
 
 // The vertex kernels are persistent 1-D grids over the FLAT list of vertices of all frames of the chunk
@@ -503,11 +507,11 @@ struct VertexParams {
 // Frames are therefore swept in order, and the grid works on neighbouring frames at any moment.
 constexpr int kMaxChunk = 256;
 
-__device__ __forceinline__ int load_frame_prefix(const int *ctrl, int nc, int stride, int *s_prefix)
+__device__ __forceinline__ int load_frame_prefix(const int *ctrl, int frame0, int nc, int stride, int *s_prefix)
 {
     __shared__ int s_total;
     for (int n = threadIdx.x; n < nc; n += blockDim.x) {
-        int m = ctrl[kCtrlCounts + n];
+        int m = ctrl[kCtrlCounts + frame0 + n];
         s_prefix[n + 1] = m > stride ? stride : m;
     }
     __syncthreads();
@@ -550,7 +554,7 @@ __device__ __forceinline__ int advance_frame(const int *s_prefix, int nc, int n,
 __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int dp1, int nc)
 {
     __shared__ int s_prefix[kMaxChunk + 1];
-    load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
+    load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -560,11 +564,11 @@ __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParam
     // 12 bytes past the last vertex in use, into rows nothing reads
     for (int n = 0; n < nc; n++) {
         const int M = s_prefix[n + 1] - s_prefix[n];
-        const size_t id0 = (size_t)n * p.stride;
+        const size_t id0 = (size_t)(p.frame0 + n) * p.stride;
         float4 *v4 = reinterpret_cast<float4 *>(p.values + id0 * p.Kp);
-        const int quads = (M * p.Kp + 3) >> 2;
+        const int quads = p.zero_values ? (M * p.Kp + 3) >> 2 : 0;
         for (int i = tid; i < quads; i += stride) v4[i] = zero4;
-        const int pairs = (M + 1) >> 1;
+        const int pairs = p.preset_links ? (M + 1) >> 1 : 0;
         for (int j = 0; j < dp1; j++) {
             int4 *l4 = reinterpret_cast<int4 *>(p.nbr + (size_t)j * p.pool + id0);
             for (int i = tid; i < pairs; i += stride) l4[i] = none4;
@@ -572,15 +576,20 @@ __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParam
     }
 }
 
-// Blur neighbours.  n1(v, j) = u  <=>  n2(u, j) = v, so ONE lookup per (vertex, axis) fills both directions;
-// every link was preset to -1 by vertex_init_kernel.  (Keeping several items per thread in flight, or looking
-// both neighbours up instead of scattering the symmetric link, measured no faster: profiles/README.md.)
+// Blur neighbours: two table lookups per (vertex, axis), one coalesced 8-byte store of the link pair; the axis-0
+// item also clears the vertex' value row for the splat.  (n1(v, j) = u <=> n2(u, j) = v, so one lookup could fill
+// both directions -- TCAMCRF_NBR_BOTH=0 -- but the scattered 4-byte store into the other vertex' links and the
+// preset pass it needs cost more than the second probe: 0.190 -> 0.150 ms per 32 noise frames, 0.049 -> 0.019 on
+// natural frames.  Keeping several items per thread in flight measured no faster: profiles/README.md.)
+#ifndef TCAMCRF_NBR_BOTH
+#define TCAMCRF_NBR_BOTH 1
+#endif
 template <int D>
 __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams p, int nc)
 {
     using Codec = KeyCodec<D>;
     __shared__ int s_prefix[kMaxChunk + 1];
-    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
+    const int total = load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
     const unsigned int mask1 = p.geom.slots1 - 1;
@@ -594,11 +603,31 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         const int m = s_prefix[n + 1] - s_prefix[n];
         const int local = i - s_prefix[n] * (D + 1);
         const int axis = local / m;
-        const int id = n * p.stride + (local - axis * m);
-        const Entry *tab = p.table + (size_t)n * p.slots;
+        const int id = (p.frame0 + n) * p.stride + (local - axis * m);
+        const Entry *tab = p.table + (size_t)(p.frame0 + n) * p.slots;
         const unsigned long long key = __ldg(p.vkey + id);
         unsigned long long k1, k2;
         Codec::neighbour_keys(key, axis, k1, k2);
+#if TCAMCRF_NBR_BOTH
+        // both neighbours are looked up (their first probes are issued together) and the link pair is written
+        // with one coalesced 8-byte store: no scattered 4-byte store into another vertex' links, and no
+        // "missing" preset pass over the link table
+        const unsigned int h1 = (unsigned int)hash_key(k1) & mask1;
+        const unsigned int h2 = (unsigned int)hash_key(k2) & mask1;
+        const uint4 e1 = __ldg(reinterpret_cast<const uint4 *>(tab + h1));
+        const uint4 e2 = __ldg(reinterpret_cast<const uint4 *>(tab + h2));
+        if (p.zero_values && axis == 0) {   // the value row of this vertex, cleared for the splat
+            float4 *row4 = reinterpret_cast<float4 *>(p.values + (size_t)id * p.Kp);
+            if ((p.Kp & 3) == 0) {
+                for (int q = 0; q < (p.Kp >> 2); q++) row4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int q = 0; q < p.Kp; q++) p.values[(size_t)id * p.Kp + q] = 0.f;
+            }
+        }
+        const int nb1 = table_lookup_from(tab, p.geom, k1, h1, 0, e1);
+        const int nb2 = table_lookup_from(tab, p.geom, k2, h2, 0, e2);
+        p.nbr[(size_t)axis * p.pool + id] = make_int2(nb1, nb2);
+#else
         const unsigned int h = (unsigned int)hash_key(k1) & mask1;
         const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
         const int nb = table_lookup_from(tab, p.geom, k1, h, 0, e);
@@ -607,6 +636,7 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
             row[id].x = nb;
             row[nb].y = id;
         }
+#endif
     }
     if (tid == 0) {
         p.ctrl[kCtrlLastCount] = total;
@@ -671,6 +701,7 @@ struct PixelParams {
     float *loss_out;        // non-null on the last chunk: receives -acc / n_norm
     float n_norm;
     int P, K, Kp;
+    int frame0;             // workspace frame of blockIdx.y == 0 (segs / as_out already point at that frame)
     long long pool;
     float alpha;
 };
@@ -703,7 +734,7 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     const int pix = blockIdx.x * kThreads + threadIdx.x;
     const bool valid = pix < p.P;
     const int lane = threadIdx.x & 31;
-    const size_t base = (size_t)n * (D + 1) * p.P + (valid ? pix : 0);
+    const size_t base = (size_t)(p.frame0 + n) * (D + 1) * p.P + (valid ? pix : 0);
     int id[D + 1];
     float w[D + 1];
     // Runs of neighbouring lanes that hit the same vertex (the common case in real frames: ~100 pixels per
@@ -766,57 +797,47 @@ struct BlurParams {
     const int2 *nbr;        // this axis: [pool]
     const int *ctrl;
     int Kp, stride;
+    int frame0;
 };
 
-// persistent 1-D grid over the flat, frame-ordered vertex list (see the note above load_frame_prefix);
-// TCAMCRF_BLUR_U items per thread and iteration (their link loads, then their gathers, are issued together)
-template <int V>
+// persistent 1-D grid over the flat, frame-ordered vertex list (see the note above load_frame_prefix).
+// Work item = (vertex, vector column); KV = Kp / V columns per vertex (0: run-time value).  The kernel is
+// issue-sensitive (ncu: 0.6 IPC per scheduler with the first version, ~140 instructions per item, most of them
+// a 64-bit division), so the (vertex, column) pair of a thread is advanced incrementally: no division in the loop.
+template <int V, int KV>
 __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int nc)
 {
-    constexpr int kU = TCAMCRF_BLUR_U;
     __shared__ int s_prefix[kMaxChunk + 1];
-    const int total = load_frame_prefix(p.ctrl, nc, p.stride, s_prefix);
-    const int kv = p.Kp / V;
-    const long long work = (long long)total * kv;
-    const long long stride = (long long)gridDim.x * kThreads;
+    const int total = load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
+    const int kv = KV > 0 ? KV : p.Kp / V;
+    const unsigned int nthreads = gridDim.x * kThreads;
+    const unsigned int tid = blockIdx.x * kThreads + threadIdx.x;
+    // thread `tid` handles items tid, tid + nthreads, ...; item i = vertex i / kv, column i % kv
+    const int dt = (int)(nthreads / (unsigned)kv), dc = (int)(nthreads % (unsigned)kv);
+    int t = (int)(tid / (unsigned)kv), c = (int)(tid % (unsigned)kv);
     int n = 0;
-    for (long long base = (long long)blockIdx.x * kThreads + threadIdx.x; base < work; base += stride * kU) {
-        size_t v[kU];
-        int c[kU];
-        int2 nb[kU];
+    const int Kp = KV > 0 ? KV * V : p.Kp;
+    for (; t < total;) {
+        n = advance_frame(s_prefix, nc, n, t);
+        const int v = (p.frame0 + n) * p.stride + (t - s_prefix[n]);
+        const int2 nb = __ldg(p.nbr + v);
+        const int col = c * V;
+        float own[V], a[V], b[V];
 #pragma unroll
-        for (int u = 0; u < kU; u++) {
-            const long long i = base + u * stride;
-            v[u] = 0;
-            c[u] = -1;
-            nb[u] = make_int2(-1, -1);
-            if (i < work) {
-                const int t = (int)(i / kv);
-                c[u] = (int)(i - (long long)t * kv) * V;
-                n = advance_frame(s_prefix, nc, n, t);
-                v[u] = (size_t)n * p.stride + (t - s_prefix[n]);
-                nb[u] = __ldg(p.nbr + v[u]);
-            }
-        }
-        float own[kU][V], a[kU][V], b[kU][V];
+        for (int e = 0; e < V; e++) a[e] = b[e] = 0.f;
+        load_vec<V>(p.src + (size_t)v * Kp + col, own);
+        if (nb.x >= 0) load_vec<V>(p.src + (size_t)nb.x * Kp + col, a);
+        if (nb.y >= 0) load_vec<V>(p.src + (size_t)nb.y * Kp + col, b);
+        float out[V];
+        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
 #pragma unroll
-        for (int u = 0; u < kU; u++) {
-#pragma unroll
-            for (int e = 0; e < V; e++) own[u][e] = a[u][e] = b[u][e] = 0.f;
-            if (c[u] >= 0) {
-                load_vec<V>(p.src + v[u] * p.Kp + c[u], own[u]);
-                if (nb[u].x >= 0) load_vec<V>(p.src + (size_t)nb[u].x * p.Kp + c[u], a[u]);
-                if (nb[u].y >= 0) load_vec<V>(p.src + (size_t)nb[u].y * p.Kp + c[u], b[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            if (c[u] < 0) continue;
-            float out[V];
-            // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
-#pragma unroll
-            for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[u][e], __fmul_rn(0.5f, __fadd_rn(a[u][e], b[u][e])));
-            store_vec<V>(p.dst + v[u] * p.Kp + c[u], out);
+        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
+        store_vec<V>(p.dst + (size_t)v * Kp + col, out);
+        t += dt;
+        c += dc;
+        if (c >= kv) {
+            c -= kv;
+            t++;
         }
     }
 }
@@ -830,7 +851,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
     const bool poisoned = p.ctrl[kCtrlStatus] != 0;
     float dot = 0.f;
     if (pix < p.P) {
-        const size_t base = (size_t)n * (D + 1) * p.P + pix;
+        const size_t base = (size_t)(p.frame0 + n) * (D + 1) * p.P + pix;
         int id[D + 1];
         float w[D + 1];
 #pragma unroll
@@ -1068,33 +1089,38 @@ static void launch_pixel(bool splat, int V, const PixelParams &pp, dim3 grid, cu
         launch_pixel_v<D, 1>(splat, pp, grid, st);
 }
 
-static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
+template <int V, int KV>
+static void launch_blur_kv(const BlurParams &bp, int nc, cudaStream_t st)
 {
-    if (V == 4)
-        blur_kernel<4><<<resident_grid(blur_kernel<4>), kThreads, 0, st>>>(bp, nc);
-    else if (V == 2)
-        blur_kernel<2><<<resident_grid(blur_kernel<2>), kThreads, 0, st>>>(bp, nc);
-    else
-        blur_kernel<1><<<resident_grid(blur_kernel<1>), kThreads, 0, st>>>(bp, nc);
+    blur_kernel<V, KV><<<resident_grid(blur_kernel<V, KV>), kThreads, 0, st>>>(bp, nc);
 }
 
-template <int D>
-static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
-                       float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
-                       int flags, cudaStream_t st)
+static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 {
-    const int logits = flags & kFlagLogits;
+    const int kv = bp.Kp / V;
+    if (V == 4) {
+        switch (kv) {
+        case 1: return launch_blur_kv<4, 1>(bp, nc, st);
+        case 2: return launch_blur_kv<4, 2>(bp, nc, st);
+        case 3: return launch_blur_kv<4, 3>(bp, nc, st);   // K = 9..12
+        case 4: return launch_blur_kv<4, 4>(bp, nc, st);
+        case 6: return launch_blur_kv<4, 6>(bp, nc, st);   // K = 21..24 (VOC's 21 classes)
+        default: return launch_blur_kv<4, 0>(bp, nc, st);
+        }
+    }
+    if (V == 2) return launch_blur_kv<2, 1>(bp, nc, st);   // Kp = 2 is the only even, non-multiple-of-4 row width
+    return launch_blur_kv<1, 1>(bp, nc, st);               // Kp = 1
+}
+
+// Stage 1 of a chunk: the lattice of `nc` frames (tables, per-pixel vertices and weights, blur links).  Needs
+// only the images.  `zero_values`: also clear the value rows in the same launch (the device path does; the
+// host path clears them group by group in value_stages).
+template <int D>
+static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int nc, char *ws,
+                          bool zero_values, cudaStream_t st)
+{
     int *ctrl = (int *)(ws + pl.off_ctrl);
     Entry *table = (Entry *)(ws + pl.off_table);
-    int *offset = (int *)(ws + pl.off_offset);
-    float *bary = (float *)(ws + pl.off_bary);
-    unsigned long long *vkey = (unsigned long long *)(ws + pl.off_vkey);
-    int2 *nbr = (int2 *)(ws + pl.off_nbr);
-    float *val0 = (float *)(ws + pl.off_val0);
-    float *val1 = (float *)(ws + pl.off_val1);
-    float *partial = (float *)(ws + pl.off_partial);
-    double *acc = (double *)(ws + pl.off_acc);
-
     {
         StageScope scope(kStPrepare, 1, st);
         prepare_kernel<<<persistent_grid(), kThreads, 0, st>>>(table, ctrl, nc, pl.chunk, pl.geom, pl.sig);
@@ -1104,9 +1130,9 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
         BuildParams bp;
         bp.images = images;
         bp.table = table;
-        bp.offset = offset;
-        bp.bary = bary;
-        bp.vkey = vkey;
+        bp.offset = (int *)(ws + pl.off_offset);
+        bp.bary = (float *)(ws + pl.off_bary);
+        bp.vkey = (unsigned long long *)(ws + pl.off_vkey);
         bp.ctrl = ctrl;
         bp.P = pl.P;
         bp.W = pl.W;
@@ -1126,13 +1152,11 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
         else
             launch_build<D, float>(bp, bgrid, st);
     }
-    const dim3 pgrid(pl.blocks_per_frame, nc);
-
     VertexParams vp;
     vp.table = table;
-    vp.vkey = vkey;
-    vp.nbr = nbr;
-    vp.values = val0;
+    vp.vkey = (unsigned long long *)(ws + pl.off_vkey);
+    vp.nbr = (int2 *)(ws + pl.off_nbr);
+    vp.values = (float *)(ws + pl.off_val0);
     vp.ctrl = ctrl;
     vp.geom = pl.geom;
     vp.slots = pl.slots;
@@ -1140,29 +1164,66 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
     vp.pool = pl.pool;
     vp.Kp = pl.Kp;
     vp.sig = pl.sig;
+    vp.frame0 = 0;
+    vp.zero_values = zero_values ? 1 : 0;
+    vp.preset_links = 1;
     {
+#if TCAMCRF_NBR_BOTH
+        StageScope scope(kStNeighbour, 1, st);
+#else
         StageScope scope(kStNeighbour, 2, st);
         vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, D + 1, nc);
+#endif
         neighbour_kernel<D><<<resident_grid(neighbour_kernel<D>), kThreads, 0, st>>>(vp, nc);
     }
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
 
+// Stage 2: splat -> blur x(d+1) -> slice (+ loss) for the frames [frame0, frame0 + nc) of a chunk whose lattice
+// is built.  segs / as_out point at frame0.  `zero_values`: the value rows were not cleared by lattice_stages.
+template <int D>
+static int value_stages(const Plan &pl, const float *segs, float *as_out, int frame0, int nc, char *ws,
+                        bool zero_values, bool want_loss, float *loss_final, float n_norm, int flags, cudaStream_t st)
+{
+    int *ctrl = (int *)(ws + pl.off_ctrl);
+    int2 *nbr = (int2 *)(ws + pl.off_nbr);
+    float *val0 = (float *)(ws + pl.off_val0);
+    float *val1 = (float *)(ws + pl.off_val1);
+    if (zero_values) {
+        VertexParams vp;
+        memset(&vp, 0, sizeof(vp));
+        vp.nbr = nbr;
+        vp.values = val0;
+        vp.ctrl = ctrl;
+        vp.stride = pl.stride;
+        vp.pool = pl.pool;
+        vp.Kp = pl.Kp;
+        vp.frame0 = frame0;
+        vp.zero_values = 1;
+        vp.preset_links = 0;
+        StageScope scope(kStSplat, 1, st);
+        vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, D + 1, nc);
+    }
+    const dim3 pgrid(pl.blocks_per_frame, nc);
     const int V = (pl.Kp % 4 == 0) ? 4 : (pl.Kp % 2 == 0) ? 2 : 1;
     PixelParams pp;
     pp.segs = segs;
-    pp.logits = logits;
+    pp.logits = flags & kFlagLogits;
     pp.as_out = as_out;
-    pp.offset = offset;
-    pp.bary = bary;
-    pp.table = table;
+    pp.offset = (int *)(ws + pl.off_offset);
+    pp.bary = (float *)(ws + pl.off_bary);
+    pp.table = (Entry *)(ws + pl.off_table);
     pp.values = val0;
-    pp.partial = want_loss ? partial : nullptr;
+    pp.partial = want_loss ? (float *)(ws + pl.off_partial) : nullptr;
     pp.ctrl = ctrl;
-    pp.acc = acc;
+    pp.acc = (double *)(ws + pl.off_acc);
     pp.loss_out = loss_final;
     pp.n_norm = n_norm;
     pp.P = pl.P;
     pp.K = pl.K;
     pp.Kp = pl.Kp;
+    pp.frame0 = frame0;
     pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
     {
@@ -1183,6 +1244,7 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
             bl.ctrl = ctrl;
             bl.Kp = pl.Kp;
             bl.stride = pl.stride;
+            bl.frame0 = frame0;
             launch_blur(V, bl, nc, st);
             float *t = src;
             src = dst;
@@ -1199,19 +1261,37 @@ static int run_chunk_d(const tcamcrf_config *cfg, const Plan &pl, bool u8, const
     return TCAMCRF_OK;
 }
 
+#define TCAMCRF_DISPATCH_D(dim, call)                                                   \
+    switch (dim) {                                                                      \
+    case 1: { constexpr int D = 1; return call; }                                       \
+    case 2: { constexpr int D = 2; return call; }                                       \
+    case 3: { constexpr int D = 3; return call; }                                       \
+    case 4: { constexpr int D = 4; return call; }                                       \
+    case 5: { constexpr int D = 5; return call; }                                       \
+    case 6: { constexpr int D = 6; return call; }                                       \
+    }                                                                                   \
+    return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", dim)
+
+static int run_lattice(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int nc, char *ws,
+                       bool zero_values, cudaStream_t st)
+{
+    TCAMCRF_DISPATCH_D(pl.D, lattice_stages<D>(cfg, pl, u8, images, nc, ws, zero_values, st));
+}
+
+static int run_values(const Plan &pl, const float *segs, float *as_out, int frame0, int nc, char *ws,
+                      bool zero_values, bool want_loss, float *loss_final, float n_norm, int flags, cudaStream_t st)
+{
+    TCAMCRF_DISPATCH_D(pl.D, value_stages<D>(pl, segs, as_out, frame0, nc, ws, zero_values, want_loss, loss_final,
+                                             n_norm, flags, st));
+}
+
 static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, const float *segs,
                      float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
                      int flags, cudaStream_t st)
 {
-    switch (pl.D) {
-    case 1: return run_chunk_d<1>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    case 2: return run_chunk_d<2>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    case 3: return run_chunk_d<3>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    case 4: return run_chunk_d<4>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    case 5: return run_chunk_d<5>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    case 6: return run_chunk_d<6>(cfg, pl, u8, images, segs, as_out, nc, ws, want_loss, loss_final, n_norm, flags, st);
-    }
-    return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", pl.D);
+    int rc = run_lattice(cfg, pl, u8, images, nc, ws, true, st);
+    if (rc) return rc;
+    return run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
 }
 
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
@@ -1304,30 +1384,37 @@ static int check_device()
     return TCAMCRF_OK;
 }
 
-// Filter (and optionally loss + gradient) with host buffers.  The batch is cut into groups of frames that
-// flow through three streams -- host->device copies, kernels, device->host copies -- so the PCIe transfers
-// of one group overlap the kernels of the next (truly asynchronous when the host buffers are pinned;
-// pageable buffers still work, the copies are then staged by the driver).
+// Filter (and optionally loss + gradient) with host buffers, pipelined over three streams (host->device
+// copies, kernels, device->host copies; truly asynchronous when the host buffers are pinned, pageable buffers
+// still work, the copies are then staged by the driver).
+//
+// The lattice depends on the images only, and the images are the small input (12 bytes per pixel against 4K
+// for the segmentations).  So the images of the whole batch go first, the lattice of the whole batch is built
+// in one full-width pass while the segmentations are still on the wire, and only the value stages (splat, blur,
+// slice, gradient) run group by group as the segmentations of a group arrive; the results of a group go back
+// while the next group computes.  The PCIe link is the bound of this path: the kernels hide behind it.
 static int host_run(const tcamcrf_config *cfg_in, const float *images, const float *segs, float *as_host,
                     float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out)
 {
     int rc = check_device();
     if (rc) return rc;
     if (!cfg_in || !images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
-    // frames per pipeline group: a few groups, each still large enough to fill the GPU
-    int want_groups = K >= 6 ? 6 : 4;   // measured on B200 (tools/e2e_sweep.sh): K=10 best at 6, K=2 at 4
+    tcamcrf_config cfg = *cfg_in;
+    if (cfg.chunk_frames <= 0 || cfg.chunk_frames > 64) cfg.chunk_frames = 64;
+    Plan pl;
+    rc = make_plan(&cfg, N, K, H, W, pl);
+    if (rc) return rc;
+    // groups of frames per chunk for the value stages (measured on B200, tools/e2e_sweep.sh)
+    int want_groups = 8;
     if (const char *env = getenv("TCAMCRF_HOST_GROUPS")) {
         const int v = atoi(env);
         if (v >= 1 && v <= 64) want_groups = v;
     }
-    int group = (N + want_groups - 1) / want_groups;
+    int group = (pl.chunk + want_groups - 1) / want_groups;
     if (group < 1) group = 1;
-    const int ngroups = (N + group - 1) / group;
-    tcamcrf_config cfg = *cfg_in;
-    if (cfg.chunk_frames <= 0 || cfg.chunk_frames > group) cfg.chunk_frames = group;
-    Plan pl;
-    rc = make_plan(&cfg, group, K, H, W, pl);
-    if (rc) return rc;
+    const int groups_per_chunk = (pl.chunk + group - 1) / group;
+    const int nchunks = (N + pl.chunk - 1) / pl.chunk;
+    const int ngroups = nchunks * groups_per_chunk;   // upper bound
     std::lock_guard<std::mutex> lock(g_host.mu);
     const size_t P = (size_t)H * W;
     const size_t img_frame = (size_t)cfg.image_stride_planes * P;   // floats per image
@@ -1349,60 +1436,75 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     cudaStream_t st = g_host.stream, s_in = g_host.s_in, s_out = g_host.s_out;
 
     if (grad_host) CUDA_TRY(cudaMemcpyAsync(d_scal, &grad_out, sizeof(float), cudaMemcpyHostToDevice, s_in));
-    for (int g = 0; g < ngroups; g++) {
-        const int n0 = g * group;
-        const int nc = (N - n0) < group ? (N - n0) : group;
-        cudaEvent_t ev_in, ev_done;
-        rc = host_event(2 * g, &ev_in);
-        if (rc) return rc;
-        rc = host_event(2 * g + 1, &ev_done);
+    int gi = 0;   // running group index
+    size_t ev_i = 0;
+    for (int c0 = 0; c0 < N; c0 += pl.chunk) {
+        const int cn = (N - c0) < pl.chunk ? (N - c0) : pl.chunk;
+        cudaEvent_t ev_img;
+        rc = host_event(ev_i++, &ev_img);
         if (rc) return rc;
         // only the planes the kernels read: the very last image may be shorter than the stride
         // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
-        size_t img_floats = (size_t)nc * img_frame;
-        if (n0 + nc == N) img_floats = ((size_t)(nc - 1) * cfg.image_stride_planes + cfg.channels) * P;
-        CUDA_TRY(cudaMemcpyAsync(d_img + n0 * img_frame, images + n0 * img_frame, img_floats * sizeof(float),
+        size_t img_floats = (size_t)cn * img_frame;
+        if (c0 + cn == N) img_floats = ((size_t)(cn - 1) * cfg.image_stride_planes + cfg.channels) * P;
+        CUDA_TRY(cudaMemcpyAsync(d_img + c0 * img_frame, images + c0 * img_frame, img_floats * sizeof(float),
                                  cudaMemcpyHostToDevice, s_in));
-        CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame, (size_t)nc * seg_frame * sizeof(float),
-                                 cudaMemcpyHostToDevice, s_in));
-        CUDA_TRY(cudaEventRecord(ev_in, s_in));
-        CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
-        rc = run_filter(&cfg, false, d_img + n0 * img_frame, d_seg + n0 * seg_frame, d_as + n0 * seg_frame,
-                        loss_host ? d_loss + g : nullptr, nc, K, H, W, (float)N, d_ws, pl.total, st);
+        CUDA_TRY(cudaEventRecord(ev_img, s_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_img, 0));
+        // status word + loss accumulator start clean (MAGIC / DIRTY persist with the workspace)
+        CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
+        rc = run_lattice(&cfg, pl, false, d_img + c0 * img_frame, cn, d_ws, false, st);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_status + g, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
-        if (grad_host) {
-            StageScope scope(kStBackward, 1, st);
-            const size_t count = (size_t)nc * seg_frame;
-            size_t blocks = (count / 4 + kThreads - 1) / kThreads;
-            if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
-            if (blocks < 1) blocks = 1;
-            loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
-                                                                        d_grad + n0 * seg_frame, count, (float)N);
+        for (int g0 = 0; g0 < cn; g0 += group, gi++) {
+            const int n0 = c0 + g0;
+            const int nc = (cn - g0) < group ? (cn - g0) : group;
+            cudaEvent_t ev_in, ev_done;
+            rc = host_event(ev_i++, &ev_in);
+            if (rc) return rc;
+            rc = host_event(ev_i++, &ev_done);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame,
+                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            CUDA_TRY(cudaEventRecord(ev_in, s_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+            // every group reports its own share of the loss (already divided by the full batch size N)
+            CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_acc, 0, sizeof(double), st));
+            rc = run_values(pl, d_seg + n0 * seg_frame, d_as + n0 * seg_frame, g0, nc, d_ws, true,
+                            loss_host != nullptr, loss_host ? d_loss + gi : nullptr, (float)N, 0, st);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(d_status + gi, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+            if (grad_host) {
+                StageScope scope(kStBackward, 1, st);
+                const size_t count = (size_t)nc * seg_frame;
+                size_t blocks = (count / 4 + kThreads - 1) / kThreads;
+                if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+                if (blocks < 1) blocks = 1;
+                loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
+                                                                            d_grad + n0 * seg_frame, count, (float)N);
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(ev_done, st));
+            CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
+            if (as_host)
+                CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
+                                         (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+            if (grad_host)
+                CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
+                                         (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ev_done, st));
-        CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
-        if (as_host)
-            CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
-                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-        if (grad_host)
-            CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
-                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
     }
-    std::vector<float> losses(ngroups, 0.f);
-    std::vector<int> status(ngroups, 0);
-    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<float> losses(gi, 0.f);
+    std::vector<int> status(gi, 0);
     if (loss_host)
-        CUDA_TRY(cudaMemcpyAsync(losses.data(), d_loss, ngroups * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, ngroups * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(losses.data(), d_loss, gi * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, gi * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaStreamSynchronize(s_out));
     int st_bits = 0;
     double total = 0.0;
-    for (int g = 0; g < ngroups; g++) {
+    for (int g = 0; g < gi; g++) {
         st_bits |= status[g];
-        total += (double)losses[g];   // every group is already divided by the full batch size N
+        total += (double)losses[g];
     }
     if (loss_host) *loss_host = (float)total;
     if (st_bits)
