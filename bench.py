@@ -266,8 +266,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     sampler = ClockSampler(local_rank)
     launches0 = lib.tcamcrf_launch_count()
-    lib.tcamcrf_profile_enable(1)
-    lib.tcamcrf_profile_read(None, None, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     barrier()
@@ -278,11 +276,20 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     barrier()
     sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    launches = lib.tcamcrf_launch_count() - launches0
+
+    # per-stage times: the same steps again with CUDA events around every stage (tcamcrf_profile_*).  Kept out of
+    # the timed region above because an event record between two kernels stops the next kernel's blocks from
+    # becoming resident while the previous one drains (programmatic dependent launch).
+    lib.tcamcrf_profile_enable(1)
+    lib.tcamcrf_profile_read(None, None, 1)
+    for i in range(args.steps):
+        step(i)
+    barrier()
     lib.tcamcrf_profile_enable(0)
     st_ms = (ctypes.c_double * len(_lib.STAGES))()
     st_ln = (ctypes.c_longlong * len(_lib.STAGES))()
     lib.tcamcrf_profile_read(st_ms, st_ln, 1)
-    launches = lib.tcamcrf_launch_count() - launches0
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:

@@ -37,6 +37,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -254,6 +255,29 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch.  The kernels of one chunk form a chain on the caller's stream; each is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks may become resident while
+// the previous kernel drains, run the part of their work that does not depend on it, and then block in
+// pdl_wait() until the previous grid has completed and its writes are visible.  Every kernel calls
+// pdl_launch_dependents() only AFTER its own pdl_wait(): when kernel X+1 starts, all blocks of X are past their
+// wait, hence X-1 and everything before it is complete.  So, ahead of its wait, a kernel may READ what kernels
+// up to X-2 (and the caller) produced, and must not write anything.
+#ifndef TCAMCRF_PDL
+#define TCAMCRF_PDL 1
+#endif
+__device__ __forceinline__ void pdl_wait()
+{
+#if TCAMCRF_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+#if TCAMCRF_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 struct BuildParams {
     const void *images;     // [N, stride_planes, P] float or u8
     Entry *table;           // [n][slots1 + slots2]
@@ -289,6 +313,8 @@ __device__ __forceinline__ float load_pixel<uint8_t>(const void *base, size_t id
 __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int nc, int chunk, TableGeom geom,
                                                            int sig)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const bool full = (ctrl[kCtrlMagic] != sig) || (ctrl[kCtrlDirty] != 0);
     const unsigned int slots = geom.slots1 + geom.slots2;
     const long long n_primary = (long long)nc * geom.slots1;
@@ -372,6 +398,9 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
 #pragma unroll
         for (int r = 0; r <= D; r++) key[r] = kEmptyKey;
     }
+    // everything above reads the caller's images only; the tables are cleared by the previous kernel
+    pdl_wait();
+    pdl_launch_dependents();
     if (!ok) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_KEY_RANGE);
 
     // Warp-cooperative insertion.  A warp holds 32 neighbouring pixels of one image row; in real frames
@@ -554,6 +583,8 @@ __device__ __forceinline__ int advance_frame(const int *s_prefix, int nc, int n,
 __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int dp1, int nc)
 {
     __shared__ int s_prefix[kMaxChunk + 1];
+    pdl_wait();
+    pdl_launch_dependents();
     load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
@@ -589,6 +620,8 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
 {
     using Codec = KeyCodec<D>;
     __shared__ int s_prefix[kMaxChunk + 1];
+    pdl_wait();   // the vertex counts come from the build kernel, the launch right before this one
+    pdl_launch_dependents();
     const int total = load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
@@ -742,26 +775,34 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     // serialise in L2.  run[r] = lanes above this one (bit i = lane+1+i) up to the end of its run.
     unsigned int heads[D + 1];
     bool any_run = false;
+    // ahead of the wait: entry indices, weights and ids come from the build kernel (two launches back), the
+    // segmentations from the caller
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         int v = -1;
         if (valid) {
             const int s = p.offset[base + (size_t)r * p.P];
             v = s < 0 ? -1 : __ldg(&p.table[s].id);
-            p.offset[base + (size_t)r * p.P] = v;
             w[r] = p.bary[base + (size_t)r * p.P];
         } else {
             w[r] = 0.f;
         }
         id[r] = v;
+    }
+    const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
+    SoftmaxStat sm = {0.f, 1.f};
+    if (L && valid) sm = softmax_stat(seg, p.K, p.P);
+    pdl_wait();   // the value rows are cleared by the previous kernel
+    pdl_launch_dependents();
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        const int v = id[r];
+        if (valid) p.offset[base + (size_t)r * p.P] = v;
         const int left = __shfl_up_sync(0xffffffffu, v, 1);
         const bool head = lane == 0 || left != v;
         heads[r] = __ballot_sync(0xffffffffu, head);
         any_run |= heads[r] != 0xffffffffu;
     }
-    const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
-    SoftmaxStat sm = {0.f, 1.f};
-    if (L && valid) sm = softmax_stat(seg, p.K, p.P);
     for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
@@ -808,6 +849,7 @@ template <int V, int KV>
 __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int nc)
 {
     __shared__ int s_prefix[kMaxChunk + 1];
+    // ahead of the wait: vertex counts (build) and links (neighbour) are older than the previous launch
     const int total = load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int kv = KV > 0 ? KV : p.Kp / V;
     const unsigned int nthreads = gridDim.x * kThreads;
@@ -817,10 +859,18 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int 
     int t = (int)(tid / (unsigned)kv), c = (int)(tid % (unsigned)kv);
     int n = 0;
     const int Kp = KV > 0 ? KV * V : p.Kp;
-    for (; t < total;) {
+    // the links of the NEXT item are fetched while the rows of the current one are in flight: one dependent
+    // round trip per item instead of two
+    int v = 0;
+    int2 nb = make_int2(-1, -1);
+    if (t < total) {
         n = advance_frame(s_prefix, nc, n, t);
-        const int v = (p.frame0 + n) * p.stride + (t - s_prefix[n]);
-        const int2 nb = __ldg(p.nbr + v);
+        v = (p.frame0 + n) * p.stride + (t - s_prefix[n]);
+        nb = __ldg(p.nbr + v);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    while (t < total) {
         const int col = c * V;
         float own[V], a[V], b[V];
 #pragma unroll
@@ -828,17 +878,23 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int 
         load_vec<V>(p.src + (size_t)v * Kp + col, own);
         if (nb.x >= 0) load_vec<V>(p.src + (size_t)nb.x * Kp + col, a);
         if (nb.y >= 0) load_vec<V>(p.src + (size_t)nb.y * Kp + col, b);
-        float out[V];
-        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
-#pragma unroll
-        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
-        store_vec<V>(p.dst + (size_t)v * Kp + col, out);
+        float *dst = p.dst + (size_t)v * Kp + col;
         t += dt;
         c += dc;
         if (c >= kv) {
             c -= kv;
             t++;
         }
+        if (t < total) {
+            n = advance_frame(s_prefix, nc, n, t);
+            v = (p.frame0 + n) * p.stride + (t - s_prefix[n]);
+            nb = __ldg(p.nbr + v);
+        }
+        float out[V];
+        // new = old + 0.5*(n1 + n2), rounded after every operation (permutohedral.cpp:547)
+#pragma unroll
+        for (int e = 0; e < V; e++) out[e] = __fadd_rn(own[e], __fmul_rn(0.5f, __fadd_rn(a[e], b[e])));
+        store_vec<V>(dst, out);
     }
 }
 
@@ -848,21 +904,27 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
     __shared__ float s_red[kThreads / 32];
     const int n = blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
-    const bool poisoned = p.ctrl[kCtrlStatus] != 0;
     float dot = 0.f;
+    int id[D + 1];
+    float w[D + 1];
+    const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
+    SoftmaxStat sm = {0.f, 1.f};
+    // ahead of the wait: vertex ids (splat), weights (build) and segmentations (caller) are all older than
+    // the previous launch (the last blur pass)
     if (pix < p.P) {
         const size_t base = (size_t)(p.frame0 + n) * (D + 1) * p.P + pix;
-        int id[D + 1];
-        float w[D + 1];
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             id[r] = p.offset[base + (size_t)r * p.P];
             // (bary * alpha) first, then * value (permutohedral.cpp:562-564)
             w[r] = __fmul_rn(p.bary[base + (size_t)r * p.P], p.alpha);
         }
-        const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
-        SoftmaxStat sm = {0.f, 1.f};
         if (L) sm = softmax_stat(seg, p.K, p.P);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    const bool poisoned = p.ctrl[kCtrlStatus] != 0;
+    if (pix < p.P) {
         float *out = p.as_out + (size_t)n * p.K * p.P + pix;
         for (int k = 0; k < p.Kp; k += V) {
             float acc[V];
@@ -1056,10 +1118,28 @@ static void scale_factors(int d, EmbedConsts &ec)
     for (int i = 0; i < d; i++) ec.scale[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev);
 }
 
+// Launches `kernel` as a programmatic dependent of the previous kernel on `st` (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+static void launch_chained(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid;
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = TCAMCRF_PDL;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
+
 template <int D, typename ImgT>
 static void launch_build(const BuildParams &bp, dim3 grid, cudaStream_t st)
 {
-    build_kernel<D, ImgT><<<grid, kThreads, 0, st>>>(bp);
+    launch_chained(build_kernel<D, ImgT>, grid, st, bp);
 }
 
 template <int D, int V>
@@ -1067,14 +1147,14 @@ static void launch_pixel_v(bool splat, const PixelParams &pp, dim3 grid, cudaStr
 {
     if (splat) {
         if (pp.logits)
-            splat_kernel<D, V, true><<<grid, kThreads, 0, st>>>(pp);
+            launch_chained(splat_kernel<D, V, true>, grid, st, pp);
         else
-            splat_kernel<D, V, false><<<grid, kThreads, 0, st>>>(pp);
+            launch_chained(splat_kernel<D, V, false>, grid, st, pp);
     } else {
         if (pp.logits)
-            slice_kernel<D, V, true><<<grid, kThreads, 0, st>>>(pp);
+            launch_chained(slice_kernel<D, V, true>, grid, st, pp);
         else
-            slice_kernel<D, V, false><<<grid, kThreads, 0, st>>>(pp);
+            launch_chained(slice_kernel<D, V, false>, grid, st, pp);
     }
 }
 
@@ -1092,7 +1172,7 @@ static void launch_pixel(bool splat, int V, const PixelParams &pp, dim3 grid, cu
 template <int V, int KV>
 static void launch_blur_kv(const BlurParams &bp, int nc, cudaStream_t st)
 {
-    blur_kernel<V, KV><<<resident_grid(blur_kernel<V, KV>), kThreads, 0, st>>>(bp, nc);
+    launch_chained(blur_kernel<V, KV>, dim3(resident_grid(blur_kernel<V, KV>)), st, bp, nc);
 }
 
 static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
@@ -1172,9 +1252,9 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         StageScope scope(kStNeighbour, 1, st);
 #else
         StageScope scope(kStNeighbour, 2, st);
-        vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, D + 1, nc);
+        launch_chained(vertex_init_kernel, dim3(resident_grid(vertex_init_kernel)), st, vp, D + 1, nc);
 #endif
-        neighbour_kernel<D><<<resident_grid(neighbour_kernel<D>), kThreads, 0, st>>>(vp, nc);
+        launch_chained(neighbour_kernel<D>, dim3(resident_grid(neighbour_kernel<D>)), st, vp, nc);
     }
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;
