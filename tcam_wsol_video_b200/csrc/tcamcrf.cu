@@ -1485,7 +1485,7 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     rc = make_plan(&cfg, N, K, H, W, pl);
     if (rc) return rc;
     // groups of frames per chunk for the value stages (measured on B200, tools/e2e_sweep.sh)
-    int want_groups = 8;
+    int want_groups = K >= 6 ? 6 : 2;
     if (const char *env = getenv("TCAMCRF_HOST_GROUPS")) {
         const int v = atoi(env);
         if (v >= 1 && v <= 64) want_groups = v;
