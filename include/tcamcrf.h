@@ -102,6 +102,21 @@ int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev,
                                float *ats_dev, int N, int K, int H, int W, void *workspace, size_t workspace_bytes,
                                void *cuda_stream);
 
+/* Lattice reuse.  tcamcrf_lattice_build runs the image-only stages (tables, per-pixel vertices and weights, blur
+ * links: Permutohedral::init, permutohedral.cpp:115-297) for N <= chunk_frames frames into `workspace`;
+ * tcamcrf_lattice_apply then filters any number of [N,K,H,W] tensors through that lattice
+ * (Permutohedral::compute, permutohedral.cpp:507-572): out = A*segs, or A^T*segs when `transposed` != 0; with
+ * loss_dev != NULL also loss_dev[0] = -sum(segs*out)/n_norm.  The workspace (sized by tcamcrf_workspace_bytes for
+ * the same cfg, N, K, H, W) IS the lattice: keep it untouched between the calls.  This is what the reference does
+ * per image inside bilateralfilter() (one init, K computes, bilateralfilter.cpp:28-37), what the exact-gradient
+ * backward needs (same lattice, transposed blur order) and what mean-field inference needs (one lattice, many
+ * iterations: DenseCRFFilter, dlib/crf/crf_post_processing.py:99-128). */
+int tcamcrf_lattice_build(const tcamcrf_config *cfg, const void *images_dev, int images_u8, int N, int K, int H,
+                          int W, void *workspace, size_t workspace_bytes, void *cuda_stream);
+int tcamcrf_lattice_apply(const tcamcrf_config *cfg, const float *segs_dev, float *out_dev, float *loss_dev, int N,
+                          int K, int H, int W, float n_norm, int transposed, void *workspace, size_t workspace_bytes,
+                          void *cuda_stream);
+
 /* Forward of the DenseCRF loss: as_dev as above and loss_dev[0] = -sum(segs*AS)/n_norm
  * (dlib/crf/dense_crf_loss.py:56-66).  n_norm is the reference's N (the local batch size). */
 int tcamcrf_loss_forward(const tcamcrf_config *cfg, const float *images_dev, const float *segs_dev, float *as_dev,

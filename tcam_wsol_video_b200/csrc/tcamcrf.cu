@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     // vertex) are summed in registers first and only the head of a run issues the RED -- same-address atomics
     // serialise in L2.  run[r] = lanes above this one (bit i = lane+1+i) up to the end of its run.
     unsigned int heads[D + 1];
+    unsigned int fresh = 0;   // bit r: offset[r] still held the entry index
     bool any_run = false;
     // ahead of the wait: entry indices, weights and ids come from the build kernel (two launches back), the
     // segmentations from the caller
@@ -781,8 +782,15 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     for (int r = 0; r <= D; r++) {
         int v = -1;
         if (valid) {
+            // offset[] holds a table entry index (>= 0) until the first splat on this lattice has turned it into
+            // the dense vertex id, stored as -2 - id (so a lattice can be applied any number of times); -1 = none
             const int s = p.offset[base + (size_t)r * p.P];
-            v = s < 0 ? -1 : __ldg(&p.table[s].id);
+            if (s >= 0) {
+                v = __ldg(&p.table[s].id);
+                fresh |= 1u << r;
+            } else if (s <= -2) {
+                v = -2 - s;
+            }
             w[r] = p.bary[base + (size_t)r * p.P];
         } else {
             w[r] = 0.f;
@@ -797,7 +805,7 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         const int v = id[r];
-        if (valid) p.offset[base + (size_t)r * p.P] = v;
+        if (fresh & (1u << r)) p.offset[base + (size_t)r * p.P] = v < 0 ? -1 : -2 - v;
         const int left = __shfl_up_sync(0xffffffffu, v, 1);
         const bool head = lane == 0 || left != v;
         heads[r] = __ballot_sync(0xffffffffu, head);
@@ -915,7 +923,8 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
         const size_t base = (size_t)(p.frame0 + n) * (D + 1) * p.P + pix;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
-            id[r] = p.offset[base + (size_t)r * p.P];
+            const int s = p.offset[base + (size_t)r * p.P];
+            id[r] = s <= -2 ? -2 - s : -1;   // see splat_kernel
             // (bary * alpha) first, then * value (permutohedral.cpp:562-564)
             w[r] = __fmul_rn(p.bary[base + (size_t)r * p.P], p.alpha);
         }
@@ -1657,6 +1666,50 @@ int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev,
                       workspace_bytes, (cudaStream_t)cuda_stream, kFlagReverseBlur);
 }
 
+// Checks shared by the two lattice entry points; the plan must describe ONE chunk holding all N frames.
+static int lattice_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, void *workspace, size_t ws_bytes,
+                        Plan &pl)
+{
+    if (!cfg || !workspace) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    int rc = make_plan(cfg, N, K, H, W, pl);
+    if (rc) return rc;
+    if (N > pl.chunk)
+        return fail(TCAMCRF_ERR_INVALID, "a lattice holds at most chunk_frames (%d) frames, got %d", pl.chunk, N);
+    if (ws_bytes < pl.total)
+        return fail(TCAMCRF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
+    if (((uintptr_t)workspace & 255) != 0) return fail(TCAMCRF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    return TCAMCRF_OK;
+}
+
+int tcamcrf_lattice_build(const tcamcrf_config *cfg, const void *images_dev, int images_u8, int N, int K, int H,
+                          int W, void *workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    if (!images_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    Plan pl;
+    int rc = lattice_plan(cfg, N, K, H, W, workspace, workspace_bytes, pl);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CUDA_TRY(cudaMemsetAsync((char *)workspace + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
+    return run_lattice(cfg, pl, images_u8 != 0, images_dev, N, (char *)workspace, false, st);
+}
+
+int tcamcrf_lattice_apply(const tcamcrf_config *cfg, const float *segs_dev, float *out_dev, float *loss_dev, int N,
+                          int K, int H, int W, float n_norm, int transposed, void *workspace, size_t workspace_bytes,
+                          void *cuda_stream)
+{
+    if (!segs_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    Plan pl;
+    int rc = lattice_plan(cfg, N, K, H, W, workspace, workspace_bytes, pl);
+    if (rc) return rc;
+    if (((uintptr_t)segs_dev & 3) || ((uintptr_t)out_dev & 3))
+        return fail(TCAMCRF_ERR_INVALID, "float buffers must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // the loss accumulator starts at zero; the status word of the build is kept (a poisoned lattice stays poisoned)
+    if (loss_dev) CUDA_TRY(cudaMemsetAsync((char *)workspace + pl.off_acc, 0, sizeof(double), st));
+    return run_values(pl, segs_dev, out_dev, 0, N, (char *)workspace, true, loss_dev != nullptr, loss_dev, n_norm,
+                      transposed ? kFlagReverseBlur : 0, st);
+}
+
 int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev, float *as_dev,
                       int N, int K, int H, int W, void *workspace, size_t workspace_bytes, void *cuda_stream)
 {
@@ -1778,7 +1831,8 @@ int tcamcrf_debug_lattice(const tcamcrf_config *cfg, const float *image_host, in
     // device layout is [r][p]; the reference's offset_/barycentric_ are [p][r]
     for (size_t px = 0; px < P; px++)
         for (int r = 0; r < dp1; r++) {
-            offset_host[px * dp1 + r] = off[(size_t)r * P + px];
+            const int sv = off[(size_t)r * P + px];
+            offset_host[px * dp1 + r] = sv <= -2 ? -2 - sv : -1;   // stored as -2 - id after the splat
             bary_host[px * dp1 + r] = bar[(size_t)r * P + px];
         }
     if (nbr_host && nbr_cap >= (size_t)dp1 * M * 2) {

@@ -42,11 +42,18 @@ class DenseCRFLossFunction(Function):
     def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False):
         n = segmentations.shape[0]
         cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
-        as_t, loss, _ = ops.crf_forward(images, segmentations.detach(), cfg, want_loss=True, n_norm=float(n))
-        ctx.AS = as_t
         ctx.N = n
         ctx.exact = bool(exact_gradient)
-        if ctx.exact:   # the transposed filter needs the lattice again: keep what rebuilds it
+        if ctx.exact and n <= 64:
+            # keep the lattice: the backward pass runs the transposed filter on it (blur axes in reverse order)
+            ctx.lattice = ops.Lattice(images, cfg, segmentations.shape[1], device=segmentations.device)
+            ctx.segs = segmentations.detach()
+            ctx.AS, loss = ctx.lattice.apply(ctx.segs, want_loss=True, n_norm=float(n))
+            return loss
+        as_t, loss, _ = ops.crf_forward(images, segmentations.detach(), cfg, want_loss=True, n_norm=float(n))
+        ctx.AS = as_t
+        if ctx.exact:   # more frames than one lattice holds: the backward pass rebuilds it
+            ctx.lattice = None
             ctx.images = images
             ctx.segs = segmentations.detach()
             ctx.sigmas = (sigma_rgb, sigma_xy)
@@ -58,8 +65,12 @@ class DenseCRFLossFunction(Function):
         if ctx.exact:
             # d/dS [-S.(A S)/N] = -(A + A^T) S / N.  The reference uses -2 A S / N (dense_crf_loss.py:73), which is
             # exact only for a symmetric A; the blur axes are applied in a fixed order, so A != A^T in general.
-            cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, ctx.sigmas[0], ctx.sigmas[1])
-            ats = ops.crf_filter_transposed(ctx.images, ctx.segs, cfg)
+            if ctx.lattice is not None:
+                ats = ctx.lattice.apply(ctx.segs, transposed=True)
+                ctx.lattice = None   # releases the workspace
+            else:
+                cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, ctx.sigmas[0], ctx.sigmas[1])
+                ats = ops.crf_filter_transposed(ctx.images, ctx.segs, cfg)
             grad_segmentation = ops.crf_backward((ctx.AS + ats) * 0.5, grad_output, float(ctx.N))
         else:
             grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N))

@@ -139,6 +139,70 @@ def crf_filter_transposed(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Co
     return out
 
 
+class Lattice:
+    """The permutohedral lattice of a batch of frames, built once and applied many times.
+
+    Owns its workspace (the lattice lives in it).  `apply(segs)` = A segs, `apply(segs, transposed=True)` = A^T segs
+    (blur axes in reverse order).  Mirrors what the reference does per image inside bilateralfilter() -- one
+    Permutohedral::init, K computes (bilateralfilter.cpp:28-37) -- and backs the exact-gradient backward and the
+    mean-field iterations of DenseCRFFilter.  At most `chunk_frames` (64) frames per lattice.
+    """
+
+    def __init__(self, images: torch.Tensor, cfg: _lib.Config, k: int, device: Optional[torch.device] = None):
+        lib = _lib.load()
+        device = torch.device(device) if device is not None else images.device
+        if device.type != "cuda":
+            raise TcamCrfError("Lattice needs a CUDA device: this package has no CPU path")
+        images, u8 = _prep_images(images, device)
+        if images.ndim != 4:
+            raise TcamCrfError(f"images must be [N,C,H,W], got {tuple(images.shape)}")
+        n, c, h, w = images.shape
+        if c < cfg.channels:
+            raise TcamCrfError(f"images have {c} planes, config needs {cfg.channels}")
+        self.cfg = _lib.Config(cfg.feat, cfg.channels, c, cfg.sigma_rgb, cfg.sigma_xy, cfg.hash_load,
+                               cfg.pool_factor, cfg.chunk_frames)
+        self.shape = (n, int(k), h, w)
+        self.device = device
+        with torch.cuda.device(device):
+            nbytes = lib.tcamcrf_workspace_bytes(byref(self.cfg), n, int(k), h, w)
+            if nbytes == 0:
+                raise TcamCrfError("tcamcrf_workspace_bytes: " + _lib.last_error())
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+            self._ws_bytes = self._ws.numel() - (self._ws_ptr - self._ws.data_ptr())
+            _lib.check(lib.tcamcrf_lattice_build(byref(self.cfg), images.data_ptr(), 1 if u8 else 0, n, int(k), h, w,
+                                                 self._ws_ptr, self._ws_bytes, _stream_ptr(device)),
+                       "tcamcrf_lattice_build")
+            # the build reads `images` asynchronously; tie their lifetime to this stream
+            images.record_stream(torch.cuda.current_stream(device))
+
+    def apply(self, segs: torch.Tensor, transposed: bool = False, want_loss: bool = False,
+              n_norm: Optional[float] = None):
+        """Returns A segs (or A^T segs); with want_loss also -sum(segs * out) / n_norm as a [1] tensor."""
+        lib = _lib.load()
+        _require_cuda(segs, "segmentations")
+        if segs.device != self.device:
+            raise TcamCrfError(f"segmentations on {segs.device}, lattice on {self.device}")
+        if tuple(segs.shape) != self.shape:
+            raise TcamCrfError(f"segmentations {tuple(segs.shape)} do not match the lattice {self.shape}")
+        segs = segs.detach().float().contiguous()
+        n, k, h, w = self.shape
+        with torch.cuda.device(self.device):
+            out = torch.empty_like(segs)
+            loss = torch.empty(1, dtype=torch.float32, device=self.device) if want_loss else None
+            _lib.check(lib.tcamcrf_lattice_apply(byref(self.cfg), segs.data_ptr(), out.data_ptr(),
+                                                 loss.data_ptr() if want_loss else None, n, k, h, w,
+                                                 float(n if n_norm is None else n_norm), 1 if transposed else 0,
+                                                 self._ws_ptr, self._ws_bytes, _stream_ptr(self.device)),
+                       "tcamcrf_lattice_apply")
+        return (out, loss) if want_loss else out
+
+    def status(self) -> Tuple[int, int]:
+        """(device status bits, vertex count); synchronises the stream."""
+        ws = self._ws if self._ws_ptr == self._ws.data_ptr() else self._ws[self._ws_ptr - self._ws.data_ptr():]
+        return workspace_status(ws)
+
+
 def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Config, n_norm: Optional[float] = None,
                        check: Optional[bool] = None):
     """Like crf_forward(want_loss=True) with segs = softmax(logits, dim=1) formed inside the kernels.
@@ -242,5 +306,5 @@ def otsu_roi(cams: torch.Tensor):
     return roi, th
 
 
-__all__ = ["otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
+__all__ = ["Lattice", "otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

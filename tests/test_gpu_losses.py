@@ -165,3 +165,72 @@ def test_exact_gradient_option(torch_cuda, oracle_mod):
     DenseCRFLoss(weight, 15.0, 100.0, 1.0)(images=raw, segmentations=s2).backward()
     want = (-2.0 * weight * a_s / n)
     assert rel_err(s2.grad.cpu().numpy(), want.cpu().numpy()) < 1e-6
+
+
+def test_lattice_reuse(torch_cuda, oracle_mod):
+    """One lattice, many filters (tcamcrf_lattice_build / _apply): equals the one-shot filter and the oracle, can
+    be applied repeatedly (the first splat turns entry indices into tagged vertex ids in place), A^T included."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import _lib, ops
+    n, k, h, w = 3, 5, 37, 52
+    raw_np = synth.make_images(n, h, w, "noise", seed=5)
+    raw = torch.from_numpy(raw_np)
+    gen = torch.Generator().manual_seed(5)
+    a = torch.rand((n, k, h, w), generator=gen).cuda()
+    b = torch.randn((n, k, h, w), generator=gen).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    lat = ops.Lattice(raw, cfg, k, device=a.device)
+    st, m = lat.status()
+    assert st == 0 and m > 0
+    want_a = oracle_mod.port_bilateralfilter_batch(raw_np, a.cpu().numpy(), n, k, h, w, 15.0, 100.0).reshape(n, k, h, w)
+    want_b = oracle_mod.port_bilateralfilter_batch(raw_np, b.cpu().numpy(), n, k, h, w, 15.0, 100.0).reshape(n, k, h, w)
+    got_a1 = lat.apply(a)
+    got_b = lat.apply(b)
+    got_a2, loss = lat.apply(a, want_loss=True, n_norm=float(n))
+    assert rel_err(got_a1.cpu().numpy(), want_a) < REL_TOL
+    assert rel_err(got_b.cpu().numpy(), want_b) < REL_TOL
+    assert rel_err(got_a2.cpu().numpy(), want_a) < REL_TOL
+    want_loss = -(a.double().cpu().numpy() * want_a.astype(np.float64)).sum() / n
+    assert abs(loss.item() - want_loss) < REL_TOL * abs(want_loss)
+    # one-shot path on the same inputs
+    one_shot, _, _ = ops.crf_forward(raw, a, cfg, want_loss=False)
+    assert rel_err(got_a1.cpu().numpy(), one_shot.cpu().numpy()) < 1e-5
+    # transposed on the kept lattice == transposed one-shot, and <b, A a> == <A^T b, a>
+    at_b = lat.apply(b, transposed=True)
+    assert rel_err(at_b.cpu().numpy(), ops.crf_filter_transposed(raw, b, cfg).cpu().numpy()) < 1e-5
+    lhs = (b.double() * got_a1.double()).sum().item()
+    rhs = (at_b.double() * a.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs)
+    with pytest.raises(_lib.TcamCrfError):
+        lat.apply(a[:, :2])
+
+
+@pytest.mark.parametrize("shape,quirk", [((2, 3, 32, 32), True), ((2, 2, 24, 40), True), ((1, 4, 30, 30), False)])
+def test_dense_crf_filter_mean_field(torch_cuda, oracle_mod, shape, quirk):
+    """DenseCRFFilter (mean-field refinement, crf_post_processing.py:33-135) against the numpy restatement of the
+    pydensecrf calls built on the oracle's filter.  Tolerance: 1e-3 absolute on probabilities -- every iteration
+    multiplies the filter's rel 1e-6 by compat=10 inside a softmax."""
+    torch = torch_cuda
+    from oracle import crf_post_processing as ocp
+    from tcam_wsol_video_b200.crf_post_processing import DenseCRFFilter
+    n, k, h, w = shape
+    raw_np = synth.make_images(n, h, w, "natural", seed=9)
+    gen = torch.Generator().manual_seed(9)
+    seg = torch.softmax(2.0 * torch.randn((n, k, h, w), generator=gen), dim=1)
+    itera = 3
+    flt = DenseCRFFilter(sigma_rgb=15.7, sigma_xy=100.2, scale_factor=1.0, itera=itera, quirk_transposed_image=quirk)
+    assert (flt.sigma_rgb, flt.sigma_xy) == (15, 100)
+    got = flt(torch.from_numpy(raw_np), seg)                       # CPU in, CPU out like the reference
+    assert got.device.type == "cpu" and got.shape == seg.shape
+    for i in range(n):
+        want = ocp.mean_field(raw_np[i], seg[i].numpy(), 15, 100, itera, oracle_mod.port_bilateralfilter_batch,
+                              quirk=quirk)
+        assert np.abs(got[i].numpy() - want).max() < 1e-3
+        assert np.abs(got[i].numpy().sum(0) - 1.0).max() < 1e-5
+    # CUDA in -> CUDA out, same numbers
+    got_cuda = flt(torch.from_numpy(raw_np).cuda(), seg.cuda())
+    assert got_cuda.is_cuda and np.abs(got_cuda.cpu().numpy() - got.numpy()).max() < 1e-4
+    # refinement does something, and itera=0 returns the (rescaled) input
+    assert np.abs(got.numpy() - seg.numpy()).max() > 1e-2
+    same = DenseCRFFilter(15, 100, 1.0, 0)(torch.from_numpy(raw_np), seg)
+    assert torch.equal(same, seg)

@@ -157,6 +157,32 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(_lib.TcamCrfError):
         loss(images=torch.zeros(1, 3, 4, 4), segmentations=torch.zeros(1, 2, 4, 4))
     assert "sigma_rgb=15.0, sigma_xy=100.0, weight=1e-07, scale_factor=1.0" == loss.extra_repr()
+    # the mean-field filter and the reusable lattice refuse a CPU-only box too; itera=0 is pure torch
+    from tcam_wsol_video_b200 import ops
+    from tcam_wsol_video_b200.crf_post_processing import DenseCRFFilter
+    segs = torch.softmax(torch.randn(1, 2, 4, 4), dim=1)
+    with pytest.raises(_lib.TcamCrfError):
+        DenseCRFFilter(15, 100, 1.0, 2)(torch.zeros(1, 3, 4, 4), segs)
+    assert torch.equal(DenseCRFFilter(15, 100, 1.0, 0)(torch.zeros(1, 3, 4, 4), segs), segs)
+    with pytest.raises(_lib.TcamCrfError):
+        ops.Lattice(torch.zeros(1, 3, 4, 4), _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0), 2)
+
+
+def test_mean_field_oracle_restatement(oracle_mod):
+    """oracle/crf_post_processing.py on its own: probabilities stay normalised, zero iterations = softmax(-U) = seg,
+    and the image pydensecrf sees is the mirrored one for square frames (crf_post_processing.py:116-118)."""
+    from oracle import crf_post_processing as ocp
+    from tcam_wsol_video_b200 import synth
+    rng = np.random.default_rng(0)
+    img = synth.make_images(1, 12, 12, "natural", seed=1)[0]
+    seen = ocp.quirk_image(img)
+    assert np.array_equal(seen, img.astype(np.uint8).transpose(0, 2, 1))
+    logits = rng.standard_normal((3, 12, 12)).astype(np.float32)
+    seg = np.exp(logits) / np.exp(logits).sum(0, keepdims=True)
+    q0 = ocp.mean_field(img, seg, 15, 100, 0, oracle_mod.port_bilateralfilter_batch)
+    assert np.abs(q0 - seg).max() < 1e-6
+    q2 = ocp.mean_field(img, seg, 15, 100, 2, oracle_mod.port_bilateralfilter_batch)
+    assert np.abs(q2.sum(0) - 1).max() < 1e-5 and np.abs(q2 - seg).max() > 1e-3
 
 
 def test_product_never_imports_the_oracle():
