@@ -214,6 +214,9 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     pl.geom.slots2 = pow2_at_least(worst / 0.75, 256);
     if (!pl.geom.slots1 || !pl.geom.slots2) return fail(TCAMCRF_ERR_INVALID, "hash table too large");
     pl.geom.window = pl.geom.slots1 < 128 ? pl.geom.slots1 : 128;
+    auto log2u = [](unsigned int v) { int l = 0; while ((1u << l) < v) l++; return (unsigned int)l; };
+    pl.geom.shift1 = 32 - log2u(pl.geom.slots1);
+    pl.geom.shift2 = 32 - log2u(pl.geom.slots2);
     pl.slots = pl.geom.slots1 + pl.geom.slots2;
     float pf = cfg->pool_factor > 0.f ? cfg->pool_factor : 1.0f;
     if (pf > 1.f) pf = 1.f;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
         slot[r] = -1;
         if (active && head) {
             pend |= 1u << r;
-            hh[r] = (unsigned int)hash_key(key[r]) & mask1;
+            hh[r] = hash_primary(key[r], p.geom);
             cur[r] = load_key_cg(tab + hh[r]);
         }
     }
@@ -645,8 +648,8 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         // both neighbours are looked up (their first probes are issued together) and the link pair is written
         // with one coalesced 8-byte store: no scattered 4-byte store into another vertex' links, and no
         // "missing" preset pass over the link table
-        const unsigned int h1 = (unsigned int)hash_key(k1) & mask1;
-        const unsigned int h2 = (unsigned int)hash_key(k2) & mask1;
+        const unsigned int h1 = hash_primary(k1, p.geom);
+        const unsigned int h2 = hash_primary(k2, p.geom);
         const uint4 e1 = __ldg(reinterpret_cast<const uint4 *>(tab + h1));
         const uint4 e2 = __ldg(reinterpret_cast<const uint4 *>(tab + h2));
         if (p.zero_values && axis == 0) {   // the value row of this vertex, cleared for the splat
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         const int nb2 = table_lookup_from(tab, p.geom, k2, h2, 0, e2);
         p.nbr[(size_t)axis * p.pool + id] = make_int2(nb1, nb2);
 #else
-        const unsigned int h = (unsigned int)hash_key(k1) & mask1;
+        const unsigned int h = hash_primary(k1, p.geom);
         const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
         const int nb = table_lookup_from(tab, p.geom, k1, h, 0, e);
         if (nb >= 0) {
