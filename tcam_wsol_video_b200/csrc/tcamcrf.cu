@@ -346,6 +346,9 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
 // Occupancy target of the build kernel: 5 blocks of 256 threads per SM caps it at 48 registers (a few
 // spills).  Measured on B200 (K=2, noise / natural frames, ms per 32-frame batch): 3 blocks 0.250 / 0.143,
 // 4 blocks 0.221 / 0.119, 5 blocks 0.214 / 0.109, 6 blocks 0.218 / 0.107, 8 blocks 0.235 / 0.107.
+#ifndef TCAMCRF_BUILD_INTERLEAVE
+#define TCAMCRF_BUILD_INTERLEAVE 1
+#endif
 #ifndef TCAMCRF_BUILD_MINBLOCKS
 #define TCAMCRF_BUILD_MINBLOCKS 5
 #endif
@@ -353,8 +356,13 @@ template <int D, typename ImgT>
 __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kernel(const BuildParams p)
 {
     using Codec = KeyCodec<D>;
+#if TCAMCRF_BUILD_INTERLEAVE
+    const int n = blockIdx.x;
+    const int pix = blockIdx.y * kThreads + threadIdx.x;
+#else
     const int n = blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
+#endif
     const bool valid = pix < p.P;
     // The reference embeds pixels four at a time and also inserts the zero-feature padding pixels of the
     // last partial block (permutohedral.cpp:173,238-251).  Those vertices are never splatted to, but they
@@ -1238,7 +1246,11 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         bp.sigma_rgb = cfg->sigma_rgb;
         bp.sigma_xy = cfg->sigma_xy;
         scale_factors(D, bp.ec);
+#if TCAMCRF_BUILD_INTERLEAVE
+        const dim3 bgrid(nc, pl.blocks_per_frame);
+#else
         const dim3 bgrid(pl.blocks_per_frame, nc);
+#endif
         if (u8)
             launch_build<D, uint8_t>(bp, bgrid, st);
         else
