@@ -184,6 +184,15 @@ long long tcamcrf_launch_count(void);
 /* out[b] = max_t cams[b,t] with torch.maximum's NaN propagation; cams_dev [B,T,HW], out_dev [B,HW]. */
 int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream);
 
+/* The same with the loader's per-frame re-normalisation first (re_normalize_cam, dlib/datasets/wsol_loader.py:
+ * 594-595, 630-635): every frame becomes nan_to_num(exp((cam + 1e-6) * h) / max over the frame) before the max.
+ * h <= 0 means no re-normalisation (sl_tc_knn_t == 0). */
+int tcam_temporal_max_renorm(const float *cams_dev, float *out_dev, int B, int T, int HW, float h, void *cuda_stream);
+
+/* Trainer.prepare_std_cams_disq (dlib/learning/train_wsol.py:417-432) in one pass: nan_to_num(nan=0, posinf=1,
+ * neginf=0) -> bilinear resize to H x W (align_corners=False) -> nan_to_num.  cams_dev [B,h,w], out_dev [B,H,W]. */
+int tcam_prepare_std_cams(const float *cams_dev, float *out_dev, int B, int h, int w, int H, int W, void *cuda_stream);
+
 /* Temporal max fused with seed selection, for a whole batch in one launch (one thread block per sample and
  * per fg/bg).  Replaces, per sample, _SFG.forward / _SBG.forward (dlib/cams/tcam_seeding.py:498-592):
  *   value = max_t cams[b,t] (* roi) + 1e-8;  candidates = the n_cand largest (fg) / smallest (bg) values,

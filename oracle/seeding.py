@@ -35,6 +35,36 @@ def temporal_max(cams: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def re_normalize_cam(cam: torch.Tensor, h: float) -> torch.Tensor:
+    """dlib/datasets/wsol_loader.py:630-635, line by line."""
+    _cam = cam + 1e-6
+    e = torch.exp(_cam * h)
+    e = e / e.max()  # in [0, 1]
+    e = torch.nan_to_num(e, nan=0.0, posinf=1., neginf=0.0)
+    return e
+
+
+def temporal_max_renorm(cams: torch.Tensor, h: float) -> torch.Tensor:
+    """cams [B,T,...]: the loader's loop (wsol_loader.py:591-600) with re_normalize_cam on every frame."""
+    outs = []
+    for b in range(cams.shape[0]):
+        std = None
+        for t in range(cams.shape[1]):
+            c = re_normalize_cam(cams[b, t], h) if h > 0 else cams[b, t]
+            std = c if std is None else torch.maximum(std, c)
+        outs.append(std)
+    return torch.stack(outs)
+
+
+def prepare_std_cams_disq(std_cams: torch.Tensor, image_size) -> torch.Tensor:
+    """dlib/learning/train_wsol.py:417-432, line by line."""
+    cams = std_cams.detach()
+    cams = torch.nan_to_num(cams, nan=0.0, posinf=1., neginf=0.0)
+    cams = torch.nn.functional.interpolate(cams, image_size, mode='bilinear', align_corners=False)
+    cams = torch.nan_to_num(cams, nan=0.0, posinf=1., neginf=0.0)
+    return cams
+
+
 def sample_fg(cam, roi, fg, max_p, max_, seed_tech):
     h, w = cam.shape
     if roi is not None:

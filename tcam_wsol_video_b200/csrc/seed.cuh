@@ -376,4 +376,104 @@ __global__ void __launch_bounds__(kSeedThreads) otsu_roi_kernel(const float *__r
     for (int i = tid; i < HW; i += kSeedThreads) out[i] = __fmul_rn(__ldg(cam + i), 255.0f) >= th ? 1 : 0;
 }
 
+
+// torch.nan_to_num(x, nan=0.0, posinf=1.0, neginf=0.0)  (wsol_loader.py:634, train_wsol.py:426,431)
+__device__ __forceinline__ float nan_to_num01(float v)
+{
+    if (v != v) return 0.0f;
+    if (v == INFINITY) return 1.0f;
+    if (v == -INFINITY) return 0.0f;
+    return v;
+}
+
+// Temporal max with the loader's optional re-normalisation of every frame's CAM first
+// (dlib/datasets/wsol_loader.py:591-600 + re_normalize_cam :630-635):
+//   e = exp((cam + 1e-6) * h);  e = e / e.max();  e = nan_to_num(e, 0, 1, 0);  out = maximum(out, e)
+// One thread block per sample; cams [B,T,HW], out [B,HW].  e.max() is torch's NaN-propagating max over the frame.
+__global__ void __launch_bounds__(kSeedThreads) temporal_max_renorm_kernel(const float *__restrict__ cams,
+                                                                           float *__restrict__ out, int T, int HW,
+                                                                           float h)
+{
+    __shared__ float s_red[kSeedThreads / 32];
+    __shared__ int s_nan[kSeedThreads / 32];
+    __shared__ float s_max;
+    __shared__ int s_anynan;
+    const int b = blockIdx.x;
+    const float *src = cams + (size_t)b * T * HW;
+    float *dst = out + (size_t)b * HW;
+    for (int t = 0; t < T; t++) {
+        const float *frame = src + (size_t)t * HW;
+        float m = -INFINITY;
+        int nan = 0;
+        for (int i = threadIdx.x; i < HW; i += kSeedThreads) {
+            const float e = expf(__fmul_rn(__fadd_rn(frame[i], 1e-6f), h));
+            nan |= (e != e);
+            m = fmaxf(m, e);   // NaN handled through the flag
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_red[threadIdx.x >> 5] = m;
+            s_nan[threadIdx.x >> 5] = nan;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float mm = -INFINITY;
+            int nn = 0;
+            for (int w = 0; w < kSeedThreads / 32; w++) {
+                mm = fmaxf(mm, s_red[w]);
+                nn |= s_nan[w];
+            }
+            s_max = mm;
+            s_anynan = nn;
+        }
+        __syncthreads();
+        const float emax = s_anynan ? __int_as_float(0x7fc00000) : s_max;
+        for (int i = threadIdx.x; i < HW; i += kSeedThreads) {
+            const float e = expf(__fmul_rn(__fadd_rn(frame[i], 1e-6f), h));
+            const float v = nan_to_num01(__fdiv_rn(e, emax));
+            if (t == 0) {
+                dst[i] = v;
+            } else {
+                const float cur = dst[i];
+                dst[i] = (cur != cur) ? cur : ((v != v) ? v : (v > cur ? v : cur));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Trainer.prepare_std_cams_disq (dlib/learning/train_wsol.py:417-432) in one pass:
+//   nan_to_num -> F.interpolate(size, mode='bilinear', align_corners=False) -> nan_to_num
+// in [B,h,w] -> out [B,H,W].  Source index and weights as in ATen's upsample_bilinear2d (area_pixel_compute_source_index
+// with align_corners=False: src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out).
+__global__ void __launch_bounds__(256) prepare_std_cams_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                               int h, int w, int H, int W, float scale_h,
+                                                               float scale_w, long long total)
+{
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+        const int x = (int)(i % W);
+        const long long r = i / W;
+        const int y = (int)(r % H);
+        const long long b = r / H;
+        float sy = scale_h * ((float)y + 0.5f) - 0.5f;
+        float sx = scale_w * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+        const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+        const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+        const float *p = in + (size_t)b * h * w + (size_t)y0 * w + x0;
+        const float v00 = nan_to_num01(__ldg(p)), v01 = nan_to_num01(__ldg(p + xp));
+        const float v10 = nan_to_num01(__ldg(p + (size_t)yp * w)), v11 = nan_to_num01(__ldg(p + (size_t)yp * w + xp));
+        const float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+        out[i] = nan_to_num01(v);
+    }
+}
+
 }  // namespace tcamcrf

@@ -2036,4 +2036,31 @@ int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int H
     return TCAMCRF_OK;
 }
 
+int tcam_temporal_max_renorm(const float *cams_dev, float *out_dev, int B, int T, int HW, float h, void *cuda_stream)
+{
+    if (!cams_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || T < 1 || HW < 1) return fail(TCAMCRF_ERR_INVALID, "B,T,HW must be positive");
+    if (!(h > 0.f)) return tcam_temporal_max(cams_dev, out_dev, B, T, HW, cuda_stream);   // wsol_loader.py:594
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    temporal_max_renorm_kernel<<<B, kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(cams_dev, out_dev, T, HW, h);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
+int tcam_prepare_std_cams(const float *cams_dev, float *out_dev, int B, int h, int w, int H, int W, void *cuda_stream)
+{
+    if (!cams_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || h < 1 || w < 1 || H < 1 || W < 1) return fail(TCAMCRF_ERR_INVALID, "sizes must be positive");
+    const long long total = (long long)B * H * W;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    // ATen: scale = (float)input_size / output_size when no scale factor is given (upsample with size=)
+    prepare_std_cams_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
+        cams_dev, out_dev, h, w, H, W, (float)h / (float)H, (float)w / (float)W, total);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
 }  // extern "C"

@@ -268,10 +268,12 @@ def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float) -
     return grad
 
 
-def temporal_cam_max(cams: torch.Tensor) -> torch.Tensor:
+def temporal_cam_max(cams: torch.Tensor, renorm_h: float = 0.0) -> torch.Tensor:
     """max over dim 1 of a CUDA float32 stack [B,T,...] -> [B,...] with torch.maximum's NaN propagation.
 
-    Mirrors the chain of ``torch.maximum`` calls in dlib/datasets/wsol_loader.py:591-600."""
+    Mirrors the chain of ``torch.maximum`` calls in dlib/datasets/wsol_loader.py:591-600.  With renorm_h > 0
+    (the loader's ``sl_tc_knn_t``) every frame first goes through ``re_normalize_cam`` (:630-635):
+    ``nan_to_num(exp((cam + 1e-6) * h) / max over the frame)``, in the same kernel."""
     lib = _lib.load()
     _require_cuda(cams, "cams")
     if cams.dtype != torch.float32:
@@ -284,8 +286,30 @@ def temporal_cam_max(cams: torch.Tensor) -> torch.Tensor:
         hw *= s
     out = torch.empty((b,) + tuple(rest), dtype=torch.float32, device=cams.device)
     with torch.cuda.device(cams.device):
-        _lib.check(lib.tcam_temporal_max(cams.data_ptr(), out.data_ptr(), b, t, hw, _stream_ptr(cams.device)),
-                   "tcam_temporal_max")
+        if renorm_h > 0:
+            _lib.check(lib.tcam_temporal_max_renorm(cams.data_ptr(), out.data_ptr(), b, t, hw, float(renorm_h),
+                                                    _stream_ptr(cams.device)), "tcam_temporal_max_renorm")
+        else:
+            _lib.check(lib.tcam_temporal_max(cams.data_ptr(), out.data_ptr(), b, t, hw, _stream_ptr(cams.device)),
+                       "tcam_temporal_max")
+    return out
+
+
+def prepare_std_cams(std_cams: torch.Tensor, image_size) -> torch.Tensor:
+    """nan_to_num -> bilinear resize (align_corners=False) -> nan_to_num in one kernel.
+
+    std_cams [B,1,h,w] CUDA float32 -> [B,1,H,W]; Trainer.prepare_std_cams_disq, dlib/learning/train_wsol.py:417-432."""
+    lib = _lib.load()
+    _require_cuda(std_cams, "std_cams")
+    if std_cams.ndim != 4 or std_cams.shape[1] != 1:
+        raise TcamCrfError(f"std_cams must be [B,1,h,w], got {tuple(std_cams.shape)}")
+    x = std_cams.detach().float().contiguous()
+    bsz, _, h, w = x.shape
+    big_h, big_w = (int(image_size), int(image_size)) if isinstance(image_size, int) else (int(image_size[0]), int(image_size[1]))
+    out = torch.empty((bsz, 1, big_h, big_w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tcam_prepare_std_cams(x.data_ptr(), out.data_ptr(), bsz, h, w, big_h, big_w,
+                                             _stream_ptr(x.device)), "tcam_prepare_std_cams")
     return out
 
 
@@ -306,5 +330,5 @@ def otsu_roi(cams: torch.Tensor):
     return roi, th
 
 
-__all__ = ["Lattice", "otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "workspace_status", "release_workspaces",
+__all__ = ["Lattice", "otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "prepare_std_cams", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

@@ -169,3 +169,50 @@ def test_seeder_computes_roi_when_none_is_given(torch_cuda):
     want = ref.tcam_seeder_forward(cam, roi.unsqueeze(1).cuda(), seed_tech=mod.seed_tech, min_=1, max_=1, min_p=0.1,
                                    max_p=0.6, ksz=3, ignore_idx=-255, use_roi=True)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("h_t", [0.0, 10.0, 50.0])
+def test_temporal_aggregation_with_renormalisation(torch_cuda, h_t):
+    """aggregate_temporal_cams = the loader's loop (wsol_loader.py:591-600) with re_normalize_cam (:630-635).
+    Plain max: bit-exact.  With the exp re-normalisation the reference runs torch's CPU exp (SLEEF), the kernel
+    CUDA's expf: equal within 2 ulp of exp -> rel 1e-6 in the ratio (tolerance stated here)."""
+    torch = torch_cuda
+    from oracle import seeding as oseed
+    from tcam_wsol_video_b200 import temporal
+    low = torch.from_numpy(synth.make_low_res_cams(6, 5, 28, 28, seed=11))        # [B,T,1,h,w]
+    low[1, 2, 0, 3, 4] = float("nan")
+    low[2, 0, 0, 0, 0] = float("inf")
+    low[3, 1, 0, 5, 5] = float("-inf")
+    want = oseed.temporal_max_renorm(low, h_t)                                     # CPU, [B,1,h,w]
+    got = temporal.aggregate_temporal_cams(low.cuda(), knn_t=h_t).cpu()
+    assert got.shape == want.shape == (6, 1, 28, 28)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    if h_t == 0.0:
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    else:
+        g, w = torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0)
+        assert (g - w).abs().max().item() <= 1e-6 * max(w.abs().max().item(), 1.0)
+    # single-frame form used by the loader
+    one = temporal.re_normalize_cam(low[0, 0].cuda(), 10.0).cpu()
+    assert (one - oseed.re_normalize_cam(low[0, 0], 10.0)).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("size", [(224, 224), (160, 288), (28, 28)])
+def test_prepare_std_cams_disq(torch_cuda, size):
+    """Fused nan_to_num -> bilinear(align_corners=False) -> nan_to_num against the trainer's three torch calls
+    (train_wsol.py:417-432).  Same source-index / weight arithmetic as ATen; tolerance 1e-6 absolute on [0,1] maps
+    (FMA contraction may differ between the two compilations)."""
+    torch = torch_cuda
+    from oracle import seeding as oseed
+    from tcam_wsol_video_b200 import temporal
+    low = torch.from_numpy(synth.make_low_res_cams(5, 1, 28, 28, seed=4))[:, 0]    # [B,1,h,w]
+    low[0, 0, 2, 3] = float("nan")
+    low[1, 0, 0, 0] = float("inf")
+    low[2, 0, 27, 27] = float("-inf")
+    want_cpu = oseed.prepare_std_cams_disq(low, size)
+    want_gpu = oseed.prepare_std_cams_disq(low.cuda(), size).cpu()
+    got = temporal.prepare_std_cams_disq(low.cuda(), size).cpu()
+    assert got.shape == want_cpu.shape
+    assert torch.isfinite(got).all()
+    assert (got - want_gpu).abs().max().item() <= 1e-6
+    assert (got - want_cpu).abs().max().item() <= 1e-6

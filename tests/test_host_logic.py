@@ -193,3 +193,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "_ref/" not in text, f
+
+
+def test_temporal_frame_pickers():
+    """left / right k-nearest frames of a shot, and the neighbourhood by mode (wsol_loader.py:448-459, 544-557)."""
+    from tcam_wsol_video_b200 import temporal as tp
+    frames = [f"f{i}" for i in range(6)]
+    assert tp.get_left_knn(frames, "f3", 2) == ["f1", "f2"]
+    assert tp.get_left_knn(frames, "f1", 4) == ["f0"]
+    assert tp.get_left_knn(frames, "f0", 4) == []
+    assert tp.get_right_knn(frames, "f3", 2) == ["f4", "f5"]
+    assert tp.get_right_knn(frames, "f4", 4) == ["f5"]
+    # reference quirk: for the last frame of a shot the slice is lframes[n-1:n] = the frame itself
+    assert tp.get_right_knn(frames, "f5", 4) == ["f5"]
+    assert tp.temporal_frames(frames, "f5", 2, tp.TIME_BEFORE_AFTER) == ["f3", "f4", "f5", "f5"]
+    assert tp.temporal_frames(frames, "f2", 4, tp.TIME_BEFORE) == ["f0", "f1", "f2"]
+    assert tp.temporal_frames(frames, "f2", 1, tp.TIME_BEFORE_AFTER) == ["f1", "f2", "f3"]
+    assert tp.temporal_frames(frames, "f2", 1, tp.TIME_AFTER) == ["f2", "f3"]
+    assert tp.temporal_frames(frames, "f2", 3, tp.TIME_INSTANT) == ["f2"]
