@@ -218,6 +218,36 @@ def test_single_image_entry_points(torch_cuda, oracle_mod):
     assert np.all(out == 7.0)
 
 
+@pytest.mark.parametrize("n,groups", [(70, None), (7, "3"), (5, "16"), (33, "1")])
+def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, monkeypatch, n, groups):
+    """Host-pointer path: the lattice of a whole chunk (<= 64 frames) is built at once, the value stages run group
+    by group with a frame offset; more than 64 frames take several chunks.  Ragged group / chunk sizes included.
+    Also the fused loss + gradient entry point (tcamcrf_loss_fwd_bwd_host)."""
+    import ctypes
+    from tcam_wsol_video_b200 import _lib
+    if groups is None:
+        monkeypatch.delenv("TCAMCRF_HOST_GROUPS", raising=False)
+    else:
+        monkeypatch.setenv("TCAMCRF_HOST_GROUPS", groups)
+    k, h, w = 3, 13, 18
+    img = synth.make_images(n, h, w, "noise", seed=n)
+    seg = synth.make_segs(n, k, h, w, seed=n)
+    want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 100.0, dim=0)
+    _assert_close(got, want, "AS (host path)")
+    lib = _lib.load()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    loss = np.zeros(1, np.float32)
+    grad = np.zeros_like(seg)
+    img_c, seg_c = np.ascontiguousarray(img), np.ascontiguousarray(seg)
+    _lib.check(lib.tcamcrf_loss_fwd_bwd_host(ctypes.byref(cfg), img_c.ctypes.data, seg_c.ctypes.data,
+                                             loss.ctypes.data, grad.ctypes.data, n, k, h, w, 0.5), "fwd_bwd_host")
+    want_loss, want_grad, _ = oracle_mod.densecrf_loss_fwd_bwd(img, seg, 15.0, 100.0, 0.5,
+                                                               oracle_mod.port_bilateralfilter_batch)
+    assert abs(float(loss[0]) - float(want_loss)) < REL_TOL * abs(float(want_loss))
+    assert rel_err(grad, want_grad) < REL_TOL
+
+
 def test_u8_images_and_chunking_give_identical_results(torch_cuda):
     """uint8 images produce the same features as float images holding the same integers, and processing the
     batch in chunks of frames does not change anything but the summation order inside the loss."""
