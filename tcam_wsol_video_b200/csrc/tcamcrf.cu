@@ -295,6 +295,7 @@ struct BuildParams {
     int stride;             // ids per frame
     long long pool;
     float sigma_rgb, sigma_xy;
+    int frame0;             // frame of block index 0 (sections of a chunk, host path)
     EmbedConsts ec;
 };
 
@@ -313,12 +314,13 @@ __device__ __forceinline__ float load_pixel<uint8_t>(const void *base, size_t id
 
 // Clears the tables of `nc` frames: always the primary tier, the overflow tier only when the workspace is
 // new (magic mismatch) or the previous use spilled into it.  Also zeroes the per-frame vertex counters.
-__global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int nc, int chunk, TableGeom geom,
-                                                           int sig)
+__global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int frame0, int nc, int chunk,
+                                                           TableGeom geom, int sig)
 {
     pdl_wait();
     pdl_launch_dependents();
-    const bool full = (ctrl[kCtrlMagic] != sig) || (ctrl[kCtrlDirty] != 0);
+    // frame0 > 0: a later section of a chunk whose first section has already dealt with the overflow tiers
+    const bool full = frame0 == 0 && ((ctrl[kCtrlMagic] != sig) || (ctrl[kCtrlDirty] != 0));
     const unsigned int slots = geom.slots1 + geom.slots2;
     const long long n_primary = (long long)nc * geom.slots1;
     // the overflow tiers of ALL frames of the workspace are cleared together: the dirty flag is per workspace
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
         if (i < n_primary) {
             n = i / geom.slots1;
             s = i - n * geom.slots1;
+            n += frame0;
         } else {
             const long long o = i - n_primary;
             n = o / geom.slots2;
@@ -339,8 +342,8 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
         }
         t4[n * slots + s] = empty;
     }
-    if (tid < nc) ctrl[kCtrlCounts + tid] = 0;
-    if (tid == 0) ctrl[kCtrlLastCount] = 0;
+    if (tid < nc) ctrl[kCtrlCounts + frame0 + tid] = 0;
+    if (tid == 0 && frame0 == 0) ctrl[kCtrlLastCount] = 0;
 }
 
 // Occupancy target of the build kernel: 5 blocks of 256 threads per SM caps it at 48 registers (a few
@@ -357,10 +360,10 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
 {
     using Codec = KeyCodec<D>;
 #if TCAMCRF_BUILD_INTERLEAVE
-    const int n = blockIdx.x;
+    const int n = p.frame0 + blockIdx.x;
     const int pix = blockIdx.y * kThreads + threadIdx.x;
 #else
-    const int n = blockIdx.y;
+    const int n = p.frame0 + blockIdx.y;
     const int pix = blockIdx.x * kThreads + threadIdx.x;
 #endif
     const bool valid = pix < p.P;
@@ -683,9 +686,10 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
 #endif
     }
     if (tid == 0) {
-        p.ctrl[kCtrlLastCount] = total;
+        // sections of one chunk run one after the other on the stream: plain read-modify-write is enough
+        p.ctrl[kCtrlLastCount] = (p.frame0 == 0 ? 0 : p.ctrl[kCtrlLastCount]) + total;
         // hand the spill state of this chunk over to the next prepare_kernel
-        p.ctrl[kCtrlDirty] = p.ctrl[kCtrlDirtyNew];
+        p.ctrl[kCtrlDirty] = (p.frame0 == 0 ? 0 : p.ctrl[kCtrlDirty]) | p.ctrl[kCtrlDirtyNew];
         p.ctrl[kCtrlDirtyNew] = 0;
         p.ctrl[kCtrlMagic] = p.sig;
     }
@@ -1216,14 +1220,14 @@ static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
 // only the images.  `zero_values`: also clear the value rows in the same launch (the device path does; the
 // host path clears them group by group in value_stages).
 template <int D>
-static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int nc, char *ws,
-                          bool zero_values, cudaStream_t st)
+static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int frame0, int nc,
+                          char *ws, bool zero_values, cudaStream_t st)
 {
     int *ctrl = (int *)(ws + pl.off_ctrl);
     Entry *table = (Entry *)(ws + pl.off_table);
     {
         StageScope scope(kStPrepare, 1, st);
-        prepare_kernel<<<persistent_grid(), kThreads, 0, st>>>(table, ctrl, nc, pl.chunk, pl.geom, pl.sig);
+        prepare_kernel<<<persistent_grid(), kThreads, 0, st>>>(table, ctrl, frame0, nc, pl.chunk, pl.geom, pl.sig);
     }
     {
         StageScope scope(kStBuild, 1, st);
@@ -1245,6 +1249,7 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         bp.pool = pl.pool;
         bp.sigma_rgb = cfg->sigma_rgb;
         bp.sigma_xy = cfg->sigma_xy;
+        bp.frame0 = frame0;
         scale_factors(D, bp.ec);
 #if TCAMCRF_BUILD_INTERLEAVE
         const dim3 bgrid(nc, pl.blocks_per_frame);
@@ -1268,7 +1273,7 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
     vp.pool = pl.pool;
     vp.Kp = pl.Kp;
     vp.sig = pl.sig;
-    vp.frame0 = 0;
+    vp.frame0 = frame0;
     vp.zero_values = zero_values ? 1 : 0;
     vp.preset_links = 1;
     {
@@ -1376,10 +1381,11 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
     }                                                                                   \
     return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d", dim)
 
-static int run_lattice(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int nc, char *ws,
-                       bool zero_values, cudaStream_t st)
+// `images` points at frame 0 of the chunk; the lattice of frames [frame0, frame0 + nc) is built.
+static int run_lattice(const tcamcrf_config *cfg, const Plan &pl, bool u8, const void *images, int frame0, int nc,
+                       char *ws, bool zero_values, cudaStream_t st)
 {
-    TCAMCRF_DISPATCH_D(pl.D, lattice_stages<D>(cfg, pl, u8, images, nc, ws, zero_values, st));
+    TCAMCRF_DISPATCH_D(pl.D, lattice_stages<D>(cfg, pl, u8, images, frame0, nc, ws, zero_values, st));
 }
 
 static int run_values(const Plan &pl, const float *segs, float *as_out, int frame0, int nc, char *ws,
@@ -1393,7 +1399,7 @@ static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const v
                      float *as_out, int nc, char *ws, bool want_loss, float *loss_final, float n_norm,
                      int flags, cudaStream_t st)
 {
-    int rc = run_lattice(cfg, pl, u8, images, nc, ws, true, st);
+    int rc = run_lattice(cfg, pl, u8, images, 0, nc, ws, true, st);
     if (rc) return rc;
     return run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
 }
@@ -1481,6 +1487,41 @@ static int host_event(size_t i, cudaEvent_t *ev)
     return TCAMCRF_OK;
 }
 
+// TCAMCRF_HOST_TRACE=1: timeline of one host_run call (timing events on the three streams), printed to stderr.
+struct HostTrace {
+    bool on = false;
+    struct Mark { const char *what; int idx; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    cudaEvent_t t0 = nullptr;
+    void begin(cudaStream_t s)
+    {
+        on = getenv("TCAMCRF_HOST_TRACE") != nullptr;
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s);
+    }
+    void mark(const char *what, int idx, cudaStream_t s)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.push_back({what, idx, e});
+    }
+    void end()
+    {
+        if (!on) return;
+        for (auto &m : marks) {
+            float ms = 0.f;
+            cudaEventSynchronize(m.ev);
+            cudaEventElapsedTime(&ms, t0, m.ev);
+            fprintf(stderr, "[host trace] %-12s %2d  %7.3f ms\n", m.what, m.idx, ms);
+            cudaEventDestroy(m.ev);
+        }
+        cudaEventDestroy(t0);
+    }
+};
+
 static int check_device()
 {
     int n = tcamcrf_device_count();
@@ -1509,16 +1550,14 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     rc = make_plan(&cfg, N, K, H, W, pl);
     if (rc) return rc;
     // groups of frames per chunk for the value stages (measured on B200, tools/e2e_sweep.sh)
-    int want_groups = K >= 6 ? 6 : 2;
+    int want_groups = K >= 6 ? 8 : 2;
     if (const char *env = getenv("TCAMCRF_HOST_GROUPS")) {
         const int v = atoi(env);
         if (v >= 1 && v <= 64) want_groups = v;
     }
     int group = (pl.chunk + want_groups - 1) / want_groups;
     if (group < 1) group = 1;
-    const int groups_per_chunk = (pl.chunk + group - 1) / group;
-    const int nchunks = (N + pl.chunk - 1) / pl.chunk;
-    const int ngroups = nchunks * groups_per_chunk;   // upper bound
+    const int ngroups = N;   // upper bound: a group holds at least one frame
     std::lock_guard<std::mutex> lock(g_host.mu);
     const size_t P = (size_t)H * W;
     const size_t img_frame = (size_t)cfg.image_stride_planes * P;   // floats per image
@@ -1539,62 +1578,83 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     char *d_ws = base + img_bytes + 3 * seg_bytes + scal_bytes;
     cudaStream_t st = g_host.stream, s_in = g_host.s_in, s_out = g_host.s_out;
 
+    HostTrace trace;
+    trace.begin(s_in);
     if (grad_host) CUDA_TRY(cudaMemcpyAsync(d_scal, &grad_out, sizeof(float), cudaMemcpyHostToDevice, s_in));
     int gi = 0;   // running group index
     size_t ev_i = 0;
     for (int c0 = 0; c0 < N; c0 += pl.chunk) {
         const int cn = (N - c0) < pl.chunk ? (N - c0) : pl.chunk;
-        cudaEvent_t ev_img;
-        rc = host_event(ev_i++, &ev_img);
-        if (rc) return rc;
-        // only the planes the kernels read: the very last image may be shorter than the stride
-        // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
-        size_t img_floats = (size_t)cn * img_frame;
-        if (c0 + cn == N) img_floats = ((size_t)(cn - 1) * cfg.image_stride_planes + cfg.channels) * P;
-        CUDA_TRY(cudaMemcpyAsync(d_img + c0 * img_frame, images + c0 * img_frame, img_floats * sizeof(float),
-                                 cudaMemcpyHostToDevice, s_in));
-        CUDA_TRY(cudaEventRecord(ev_img, s_in));
-        CUDA_TRY(cudaStreamWaitEvent(st, ev_img, 0));
         // status word + loss accumulator start clean (MAGIC / DIRTY persist with the workspace)
         CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
-        rc = run_lattice(&cfg, pl, false, d_img + c0 * img_frame, cn, d_ws, false, st);
-        if (rc) return rc;
-        for (int g0 = 0; g0 < cn; g0 += group, gi++) {
-            const int n0 = c0 + g0;
-            const int nc = (cn - g0) < group ? (cn - g0) : group;
-            cudaEvent_t ev_in, ev_done;
-            rc = host_event(ev_i++, &ev_in);
+        // Sections: the lattice of a first, small section is built as soon as its images are in, so that the first
+        // results start their way back early -- the copy back runs at link speed from then on and is what ends
+        // last.  The rest of the chunk forms the second section (built at full width).
+        // Measured on B200, 32 frames (frames/s): K=10: one section 14.6 k, first section 4 frames 15.1 k;
+        // K=2: one section 28.2 k, first section 16 frames 32.5 k.
+        int sec0 = cn >= 16 ? (K >= 6 ? (cn + 7) / 8 : (cn + 1) / 2) : cn;
+        if (const char *env = getenv("TCAMCRF_HOST_SECTION0")) {
+            const int v = atoi(env);
+            if (v >= 1) sec0 = v < cn ? v : cn;
+        }
+        for (int f0 = 0, fn = 0; f0 < cn; f0 += fn) {
+            fn = f0 == 0 ? sec0 : cn - f0;
+            cudaEvent_t ev_img;
+            rc = host_event(ev_i++, &ev_img);
             if (rc) return rc;
-            rc = host_event(ev_i++, &ev_done);
+            // only the planes the kernels read: the very last image may be shorter than the stride
+            // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
+            size_t img_floats = (size_t)fn * img_frame;
+            if (c0 + f0 + fn == N) img_floats = ((size_t)(fn - 1) * cfg.image_stride_planes + cfg.channels) * P;
+            CUDA_TRY(cudaMemcpyAsync(d_img + (size_t)(c0 + f0) * img_frame, images + (size_t)(c0 + f0) * img_frame,
+                                     img_floats * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            CUDA_TRY(cudaEventRecord(ev_img, s_in));
+            trace.mark("images in", c0 + f0, s_in);
+            CUDA_TRY(cudaStreamWaitEvent(st, ev_img, 0));
+            rc = run_lattice(&cfg, pl, false, d_img + (size_t)c0 * img_frame, f0, fn, d_ws, false, st);
             if (rc) return rc;
-            CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame,
-                                     (size_t)nc * seg_frame * sizeof(float), cudaMemcpyHostToDevice, s_in));
-            CUDA_TRY(cudaEventRecord(ev_in, s_in));
-            CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
-            // every group reports its own share of the loss (already divided by the full batch size N)
-            CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_acc, 0, sizeof(double), st));
-            rc = run_values(pl, d_seg + n0 * seg_frame, d_as + n0 * seg_frame, g0, nc, d_ws, true,
-                            loss_host != nullptr, loss_host ? d_loss + gi : nullptr, (float)N, 0, st);
-            if (rc) return rc;
-            CUDA_TRY(cudaMemcpyAsync(d_status + gi, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
-            if (grad_host) {
-                StageScope scope(kStBackward, 1, st);
-                const size_t count = (size_t)nc * seg_frame;
-                size_t blocks = (count / 4 + kThreads - 1) / kThreads;
-                if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
-                if (blocks < 1) blocks = 1;
-                loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
-                                                                            d_grad + n0 * seg_frame, count, (float)N);
+            trace.mark("lattice", c0 + f0, st);
+            for (int g0 = f0, nc = 0; g0 < f0 + fn; g0 += nc, gi++) {
+                const int n0 = c0 + g0;
+                const int left = f0 + fn - g0;
+                nc = left < group ? left : group;
+                cudaEvent_t ev_in, ev_done;
+                rc = host_event(ev_i++, &ev_in);
+                if (rc) return rc;
+                rc = host_event(ev_i++, &ev_done);
+                if (rc) return rc;
+                CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame,
+                                         (size_t)nc * seg_frame * sizeof(float), cudaMemcpyHostToDevice, s_in));
+                CUDA_TRY(cudaEventRecord(ev_in, s_in));
+                trace.mark("segs in", gi, s_in);
+                CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+                // every group reports its own share of the loss (already divided by the full batch size N)
+                CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_acc, 0, sizeof(double), st));
+                rc = run_values(pl, d_seg + n0 * seg_frame, d_as + n0 * seg_frame, g0, nc, d_ws, true,
+                                loss_host != nullptr, loss_host ? d_loss + gi : nullptr, (float)N, 0, st);
+                if (rc) return rc;
+                CUDA_TRY(cudaMemcpyAsync(d_status + gi, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                if (grad_host) {
+                    StageScope scope(kStBackward, 1, st);
+                    const size_t count = (size_t)nc * seg_frame;
+                    size_t blocks = (count / 4 + kThreads - 1) / kThreads;
+                    if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
+                    if (blocks < 1) blocks = 1;
+                    loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
+                                                                                d_grad + n0 * seg_frame, count, (float)N);
+                }
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(ev_done, st));
+                trace.mark("computed", gi, st);
+                CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
+                if (as_host)
+                    CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
+                                             (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+                if (grad_host)
+                    CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
+                                             (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+                trace.mark("results out", gi, s_out);
             }
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(ev_done, st));
-            CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
-            if (as_host)
-                CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
-                                         (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-            if (grad_host)
-                CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
-                                         (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         }
     }
     std::vector<float> losses(gi, 0.f);
@@ -1604,6 +1664,7 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, gi * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaStreamSynchronize(s_out));
+    trace.end();
     int st_bits = 0;
     double total = 0.0;
     for (int g = 0; g < gi; g++) {
@@ -1705,7 +1766,7 @@ int tcamcrf_lattice_build(const tcamcrf_config *cfg, const void *images_dev, int
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CUDA_TRY(cudaMemsetAsync((char *)workspace + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
-    return run_lattice(cfg, pl, images_u8 != 0, images_dev, N, (char *)workspace, false, st);
+    return run_lattice(cfg, pl, images_u8 != 0, images_dev, 0, N, (char *)workspace, false, st);
 }
 
 int tcamcrf_lattice_apply(const tcamcrf_config *cfg, const float *segs_dev, float *out_dev, float *loss_dev, int N,
