@@ -391,6 +391,38 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception as exc:  # context only; never fail the headline line
             extra["tcam_seed_crf_step_natural_k2"] = {"error": repr(exc)[:200]}
 
+        # BASELINE configs[3]: lattice-size stress at 448x448 -- the 5-D colour lattice (x, y, r, g, b) and the 3-D
+        # grayscale one (x, y, gray), 8 frames, K=2, noise frames (largest lattices), fwd+bwd like the headline.
+        try:
+            from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLossFunction  # noqa: F401
+            n4, k4, s4 = 8, 2, 448
+            img4 = torch.from_numpy(synth.make_images(n4, s4, s4, "noise", seed=11)).to(dev)
+            seg4 = torch.from_numpy(synth.make_segs(n4, k4, s4, s4, seed=11)).to(dev)
+            for name, feat_channels in (("xyrgb_5d", 3), ("xygray_3d", 1)):
+                cfg4 = _lib.make_config(_lib.FEAT_XY_RGB, feat_channels, SIGMA_RGB, SIGMA_XY)
+                g_one = torch.ones(1, device=dev)
+
+                def step4():
+                    as4, _, _ = ops.crf_forward(img4, seg4, cfg4, want_loss=True, n_norm=float(n4))
+                    ops.crf_backward(as4, g_one, float(n4))
+
+                for _ in range(5):
+                    step4()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(30):
+                    step4()
+                e1.record()
+                torch.cuda.synchronize()
+                _, ws4 = None, ops.crf_forward(img4, seg4, cfg4, check=True)[2]
+                _, m4 = ops.workspace_status(ws4)
+                extra[f"noise_448_{name}_k2"] = {"value": n4 * 30 / (e0.elapsed_time(e1) / 1e3), "unit": UNIT,
+                                                 "steps": 30, "frames": n4, "vertices_per_frame": m4 / n4}
+            del img4, seg4
+        except Exception as exc:
+            extra["noise_448"] = {"error": repr(exc)[:200]}
+
     if rank != 0:
         return
 
@@ -429,6 +461,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                  "achieved": frame_bytes(P, D, K, M) * value / world / 1e9,
                                  "frac": frame_bytes(P, D, K, M) * value / world / 1e9 / peak},
                     "stages": stages}
+        if roofline["frac"] > 1.0:
+            roofline["note"] = ("frac > 1: SURVEY 8d's algorithmic bytes of this stage count the neighbour-row gathers, "
+                                "which the L2 serves; `traffic` is the DRAM traffic per launch (ncu), "
+                                "`pipeline.frac` the whole step against the HBM peak")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
