@@ -1,22 +1,24 @@
 // tcamcrf.cu -- kernels + C ABI of libtcamcrf.so (see include/tcamcrf.h).
 //
-// Pipeline for one chunk of frames (all launches on the caller's stream):
+// Pipeline for one chunk of frames (all launches on the caller's stream, chained by programmatic dependent
+// launch: each kernel runs what does not depend on its predecessor ahead of griddepcontrol.wait):
 //
+//   -- lattice stages (need the images only) --
 //   prepare_kernel       clears the primary tier of the frame tables (and the overflow
 //                        tier only if the previous use spilled into it), zeroes counters
 //   build_kernel<D>      per pixel: features -> embedding -> d+1 packed keys ->
 //                        warp-deduplicated (runs of equal keys) insert into the frame's two-tier table
 //                        (all first probes issued before any is consumed);
 //                        warp-aggregated allocation of dense, per-frame-contiguous ids
-//   vertex_init_kernel   zeroes the value rows of the vertices in use, presets links to "missing"
-//   neighbour_kernel<D>  per (vertex, axis): ONE table lookup (the n1 neighbour); the
-//                        symmetric n2 link is written from the other side
-//   splat_kernel<V>      per pixel: entry -> dense id (kept for slice), vector
+//   neighbour_kernel<D>  per (vertex, axis): two table lookups (n1, n2), one 8-byte store of the link
+//                        pair; the axis-0 item clears the vertex' value row
+//   -- value stages (any number of times on one lattice) --
+//   vertex_init_kernel   (host path / lattice re-use only) zeroes the value rows again
+//   splat_kernel<V>      per pixel: entry -> dense id (kept, tagged, for slice and later splats), vector
 //                        RED.ADD of w * seg[k] into values[id][0..Kp)
 //   blur_kernel<V> x(d+1) per (vertex, k-vector): new = old + 0.5*(old[n1]+old[n2])
 //   slice_kernel<V>      per pixel: AS[k] = sum_r (bary_r*alpha) * values[id_r][k];
-//                        block partial of seg . AS
-//   loss_reduce / loss_finish
+//                        block partial of seg . AS; the last block folds the partials into the loss
 //
 // Reference functions replaced: bilateralfilter_batch / bilateralfilter /
 // initializePermutohedral (bilateralfilter.cpp:4-55), the colour variants
@@ -541,7 +543,7 @@ struct VertexParams {
     int sig;
     int frame0;             // first frame of the chunk this launch works on (0 unless the host path runs the
                             // value stages group by group on a lattice built for the whole batch)
-    int zero_values, preset_links;   // what vertex_init_kernel clears
+    int zero_values;        // neighbour_kernel: also clear the value rows
 };
 
 // The vertex kernels are persistent 1-D grids over the FLAT list of vertices of all frames of the chunk
@@ -593,8 +595,9 @@ __device__ __forceinline__ int advance_frame(const int *s_prefix, int nc, int n,
     return n;
 }
 
-// Zeroes the value rows and presets every neighbour link of the vertices in use to "missing".
-__global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int dp1, int nc)
+// Zeroes the value rows of the vertices in use (host path and lattice re-use: the neighbour kernel clears them
+// only once, right after the build).
+__global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParams p, int nc)
 {
     __shared__ int s_prefix[kMaxChunk + 1];
     pdl_wait();
@@ -603,7 +606,6 @@ __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParam
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int4 none4 = make_int4(-1, -1, -1, -1);
     // pure streaming stores: walk the frames one after the other (the counts sit in shared memory), 16 bytes
     // per store; a frame's rows start 16-byte aligned (stride is a multiple of 32) and a store may run up to
     // 12 bytes past the last vertex in use, into rows nothing reads
@@ -611,24 +613,16 @@ __global__ void __launch_bounds__(kThreads) vertex_init_kernel(const VertexParam
         const int M = s_prefix[n + 1] - s_prefix[n];
         const size_t id0 = (size_t)(p.frame0 + n) * p.stride;
         float4 *v4 = reinterpret_cast<float4 *>(p.values + id0 * p.Kp);
-        const int quads = p.zero_values ? (M * p.Kp + 3) >> 2 : 0;
+        const int quads = (M * p.Kp + 3) >> 2;
         for (int i = tid; i < quads; i += stride) v4[i] = zero4;
-        const int pairs = p.preset_links ? (M + 1) >> 1 : 0;
-        for (int j = 0; j < dp1; j++) {
-            int4 *l4 = reinterpret_cast<int4 *>(p.nbr + (size_t)j * p.pool + id0);
-            for (int i = tid; i < pairs; i += stride) l4[i] = none4;
-        }
     }
 }
 
 // Blur neighbours: two table lookups per (vertex, axis), one coalesced 8-byte store of the link pair; the axis-0
 // item also clears the vertex' value row for the splat.  (n1(v, j) = u <=> n2(u, j) = v, so one lookup could fill
-// both directions -- TCAMCRF_NBR_BOTH=0 -- but the scattered 4-byte store into the other vertex' links and the
-// preset pass it needs cost more than the second probe: 0.190 -> 0.150 ms per 32 noise frames, 0.049 -> 0.019 on
-// natural frames.  Keeping several items per thread in flight measured no faster: profiles/README.md.)
-#ifndef TCAMCRF_NBR_BOTH
-#define TCAMCRF_NBR_BOTH 1
-#endif
+// both directions, but the scattered 4-byte store into the other vertex' links and the preset pass it needs cost
+// more than the second probe: 0.190 -> 0.150 ms per 32 noise frames, 0.049 -> 0.019 on natural frames.  Keeping
+// several items per thread in flight measured no faster: profiles/README.md.)
 template <int D>
 __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams p, int nc)
 {
@@ -655,7 +649,6 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         const unsigned long long key = __ldg(p.vkey + id);
         unsigned long long k1, k2;
         Codec::neighbour_keys(key, axis, k1, k2);
-#if TCAMCRF_NBR_BOTH
         // both neighbours are looked up (their first probes are issued together) and the link pair is written
         // with one coalesced 8-byte store: no scattered 4-byte store into another vertex' links, and no
         // "missing" preset pass over the link table
@@ -674,16 +667,6 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         const int nb1 = table_lookup_from(tab, p.geom, k1, h1, 0, e1);
         const int nb2 = table_lookup_from(tab, p.geom, k2, h2, 0, e2);
         p.nbr[(size_t)axis * p.pool + id] = make_int2(nb1, nb2);
-#else
-        const unsigned int h = hash_primary(k1, p.geom);
-        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
-        const int nb = table_lookup_from(tab, p.geom, k1, h, 0, e);
-        if (nb >= 0) {
-            int2 *row = p.nbr + (size_t)axis * p.pool;
-            row[id].x = nb;
-            row[nb].y = id;
-        }
-#endif
     }
     if (tid == 0) {
         // sections of one chunk run one after the other on the stream: plain read-modify-write is enough
@@ -1275,14 +1258,8 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
     vp.sig = pl.sig;
     vp.frame0 = frame0;
     vp.zero_values = zero_values ? 1 : 0;
-    vp.preset_links = 1;
     {
-#if TCAMCRF_NBR_BOTH
         StageScope scope(kStNeighbour, 1, st);
-#else
-        StageScope scope(kStNeighbour, 2, st);
-        launch_chained(vertex_init_kernel, dim3(resident_grid(vertex_init_kernel)), st, vp, D + 1, nc);
-#endif
         launch_chained(neighbour_kernel<D>, dim3(resident_grid(neighbour_kernel<D>)), st, vp, nc);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1310,9 +1287,8 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
         vp.Kp = pl.Kp;
         vp.frame0 = frame0;
         vp.zero_values = 1;
-        vp.preset_links = 0;
         StageScope scope(kStSplat, 1, st);
-        vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, D + 1, nc);
+        vertex_init_kernel<<<resident_grid(vertex_init_kernel), kThreads, 0, st>>>(vp, nc);
     }
     const dim3 pgrid(pl.blocks_per_frame, nc);
     const int V = (pl.Kp % 4 == 0) ? 4 : (pl.Kp % 2 == 0) ? 2 : 1;

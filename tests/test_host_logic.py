@@ -123,6 +123,15 @@ def test_workspace_sizing_and_argument_validation():
     assert lib.tcamcrf_filter(ctypes.byref(cfg), None, None, None, 1, 2, 8, 8, None, 0, None) == 1
     assert lib.tcamcrf_loss_backward(None, None, None, 16, 1.0, None) == 1
     assert lib.tcam_temporal_max(None, None, 1, 1, 1, None) == 1
+    assert lib.tcam_temporal_max_renorm(None, None, 1, 1, 1, 10.0, None) == 1
+    assert lib.tcam_prepare_std_cams(None, None, 1, 28, 28, 224, 224, None) == 1
+    # lattice re-use API: one lattice holds at most chunk_frames (64) frames; pointers and workspace are checked
+    assert lib.tcamcrf_lattice_build(ctypes.byref(cfg), None, 0, 1, 2, 8, 8, None, 0, None) == 1
+    assert lib.tcamcrf_lattice_apply(ctypes.byref(cfg), None, None, None, 1, 2, 8, 8, 1.0, 0, None, 0, None) == 1
+    fake = ctypes.c_void_p(256)   # never dereferenced: the frame-count check comes first
+    assert lib.tcamcrf_lattice_build(ctypes.byref(cfg), fake, 0, 65, 2, 8, 8, fake, 1 << 40, None) == 1
+    assert b"at most" in lib.tcamcrf_last_error()
+    assert lib.tcamcrf_lattice_build(ctypes.byref(cfg), fake, 0, 2, 2, 8, 8, fake, 16, None) == 2   # workspace too small
 
 
 def test_dropin_modules_validate_like_the_swig_typemaps():
