@@ -184,6 +184,17 @@ long long tcamcrf_launch_count(void);
 /* out[b] = max_t cams[b,t] with torch.maximum's NaN propagation; cams_dev [B,T,HW], out_dev [B,HW]. */
 int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int HW, void *cuda_stream);
 
+/* ROI by connected components, one thread block per sample: GetRoiSingleCam.__call__ with roi_method
+ * 'roi_high_density' (largest_only = 0) or 'roi_largest' (1), dlib/cams/tcam_seeding.py:347-412.
+ * cams_dev [B,H*W]; thresh_dev [B] on the 0..255 scale (tcam_otsu_roi's thresholds, or thresh*255);
+ * roi_dev [B,H*W] int64 0/1: the selected 4-connected component of cam*255 >= thresh; bbox_dev [B,4] int32
+ * x0,y0,x1,y1 (cv2.boundingRect convention of dlib/utils/wsol.py:133-137); bbox_mask_dev [B,H*W] float 0/1.
+ * p_min_area: a densest component smaller than p_min_area*H*W gives way to the largest one. */
+size_t tcam_roi_components_scratch_bytes(int B, int H, int W);
+int tcam_roi_components(const float *cams_dev, const float *thresh_dev, long long *roi_dev, float *bbox_mask_dev,
+                        int *bbox_dev, int B, int H, int W, int largest_only, float p_min_area, void *scratch_dev,
+                        size_t scratch_bytes, void *cuda_stream);
+
 /* The same with the loader's per-frame re-normalisation first (re_normalize_cam, dlib/datasets/wsol_loader.py:
  * 594-595, 630-635): every frame becomes nan_to_num(exp((cam + 1e-6) * h) / max over the frame) before the max.
  * h <= 0 means no re-normalisation (sl_tc_knn_t == 0). */

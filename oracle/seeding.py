@@ -187,3 +187,58 @@ def roi_all_single_cam(cam):
         th = threshold_otsu_skimage(cam_)
     blobs = (_cam * 255. >= th).astype(int)
     return blobs.astype(np.int64), float(th)
+
+
+def roi_components_single_cam(cam, roi_method, p_min_area_roi, thresh=None):
+    """GetRoiSingleCam.__call__ for roi_method 'roi_high_density' / 'largest' (dlib/cams/tcam_seeding.py:325-417),
+    line by line, with the two third-party calls restated:
+      * skimage.measure.label(blobs, background=0, connectivity=1) -> scipy.ndimage.label with the 4-neighbour
+        structure (same components; both number them in raster order of their first pixel);
+      * cv2.findContours(RETR_EXTERNAL) + cv2.boundingRect on ONE 4-connected component -> its bounding rectangle
+        (x, y, w, h) = (min col, min row, extent, extent), then dlib/utils/wsol.py:133-137.
+    Returns (final_roi int64 [h,w], bbox_mask float32 [h,w], bbox [1,4] x0y0x1y1)."""
+    import numpy as np
+    from scipy import ndimage
+    _cam = np.asarray(cam, dtype=np.float32)
+    h, w = _cam.shape
+    if thresh is None:
+        cam_ = np.floor(_cam * 255.)
+        _thresh = 0. if cam_.min() == cam_.max() else threshold_otsu_skimage(cam_)
+    else:
+        _thresh = thresh * 255.
+    blobs = (_cam * 255. >= np.float32(_thresh)).astype(int)
+    four = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    blobs_labels, _ = ndimage.label(blobs, structure=four)
+    labels = np.unique(blobs_labels)
+    if labels.size == 1:
+        final_roi = blobs.astype(float)
+    else:
+        label_density, label_area = dict(), dict()
+        min_area = (h * w) * p_min_area_roi
+        for l in labels:
+            if l == 0:
+                continue
+            s_roi = (blobs_labels == l).astype(float)
+            s_cam = _cam * s_roi
+            s_roi_area = s_roi.sum()
+            label_density[l] = s_cam.sum() / s_roi_area
+            label_area[l] = s_roi_area
+        if roi_method == 'roi_high_density':
+            l_roi = max(label_density, key=label_density.get)
+            if label_area[l_roi] < min_area:
+                l_roi = max(label_area, key=label_area.get)
+        elif roi_method == 'largest':
+            l_roi = max(label_area, key=label_area.get)
+        else:
+            raise NotImplementedError(roi_method)
+        final_roi = (blobs_labels == l_roi).astype(float)
+    ys, xs = np.nonzero(final_roi > 0.5)
+    if ys.size == 0:
+        bbox = np.array([[0, 0, 0, 0]])
+    else:
+        x, y, bw, bh = xs.min(), ys.min(), xs.max() - xs.min() + 1, ys.max() - ys.min() + 1
+        bbox = np.array([[x, y, min(x + bw, w - 1), min(y + bh, h - 1)]])
+    bbox_mask = np.zeros((h, w), dtype=np.float32)
+    x0, y0, x1, y1 = bbox.flatten()
+    bbox_mask[y0:y1, x0:x1] = 1.
+    return final_roi.astype(np.int64), bbox_mask, bbox.astype(np.float32)

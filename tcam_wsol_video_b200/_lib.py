@@ -114,6 +114,8 @@ SIGNATURES = {
     "tcamcrf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
     "tcamcrf_launch_count": (ctypes.c_longlong, []),
     "tcam_temporal_max": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tcam_roi_components_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tcam_roi_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "tcam_temporal_max_renorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "tcam_prepare_std_cams": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tcam_seed_select": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

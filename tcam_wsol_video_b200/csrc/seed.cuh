@@ -377,6 +377,196 @@ __global__ void __launch_bounds__(kSeedThreads) otsu_roi_kernel(const float *__r
 }
 
 
+// ---------------------------------------------------------------------------------------------------------
+// ROI by connected components: GetRoiSingleCam.__call__ with roi_method 'roi_high_density' / 'roi_largest'
+// (dlib/cams/tcam_seeding.py:347-412).  The reference runs on the CPU per sample:
+//   blobs = cam*255 >= thresh;  skimage.measure.label(blobs, connectivity=1)   (4-connected components)
+//   per component: area, density = sum(cam over the component) / area          (float64)
+//   high density: the densest component, unless its area < p_min_area*H*W -> the largest one;  largest: the largest
+//   final_roi = that component;  bbox = cv2.boundingRect of its (single) external contour, x1/y1 clamped
+//   (dlib/utils/wsol.py:133-137);  bbox_mask[y0:y1, x0:x1] = 1
+// Here: one thread block per sample.  Components by union-find on the pixel grid (label = smallest pixel index of
+// the component, merged with atomicMin like ECL-CC), so "first label" ties resolve like skimage's raster-order
+// numbering; areas with integer atomics, sums with float64 atomics (the order of the additions is not the
+// reference's pairwise one: densities agree to ~1e-15 relative; exact ties go to the first component).
+// scratch: labels int[B*HW], area int[B*HW], sum double[B*HW].
+__device__ __forceinline__ int cc_find(const int *label, int x)
+{
+    int p = label[x];
+    while (p != x) {
+        x = p;
+        p = label[x];
+    }
+    return x;
+}
+
+__device__ __forceinline__ void cc_union(int *label, int a, int b)
+{
+    while (true) {
+        a = cc_find(label, a);
+        b = cc_find(label, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        // hang the larger root under the smaller one; if somebody re-rooted `a` meanwhile, retry from there
+        const int old = atomicMin(label + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct RoiBest {
+    double key;   // density or area
+    int idx;      // root pixel index; smaller wins ties
+};
+__device__ __forceinline__ RoiBest roi_better(RoiBest x, RoiBest y)
+{
+    if (y.idx < 0) return x;
+    if (x.idx < 0) return y;
+    if (y.key > x.key || (y.key == x.key && y.idx < x.idx)) return y;
+    return x;
+}
+
+__global__ void __launch_bounds__(kSeedThreads) roi_components_kernel(const float *__restrict__ cams,
+                                                                      const float *__restrict__ thresh,
+                                                                      long long *__restrict__ roi,
+                                                                      float *__restrict__ bbox_mask,
+                                                                      int *__restrict__ bbox, int *labels, int *area,
+                                                                      double *sum, int H, int W, int largest_only,
+                                                                      double min_area)
+{
+    __shared__ RoiBest s_best[2][kSeedThreads / 32];
+    __shared__ int s_sel;
+    __shared__ int s_box[4][kSeedThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int HW = H * W;
+    const float *cam = cams + (size_t)b * HW;
+    int *lab = labels + (size_t)b * HW;
+    int *ar = area + (size_t)b * HW;
+    double *sm = sum + (size_t)b * HW;
+    const float th = thresh[b];
+
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        lab[i] = __fmul_rn(cam[i], 255.0f) >= th ? i : -1;
+        ar[i] = 0;
+        sm[i] = 0.0;
+    }
+    __syncthreads();
+    // 4-connectivity: merge with the left and the upper neighbour
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        if (lab[i] < 0) continue;
+        const int y = i / W, x = i - y * W;
+        if (x > 0 && lab[i - 1] >= 0) cc_union(lab, i, i - 1);
+        if (y > 0 && lab[i - W] >= 0) cc_union(lab, i, i - W);
+    }
+    __syncthreads();
+    // flatten + per-component statistics
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        if (lab[i] < 0) continue;
+        const int r = cc_find(lab, i);
+        lab[i] = r;   // only shortens paths: concurrent finds stay correct
+        atomicAdd(ar + r, 1);
+        atomicAdd(sm + r, (double)cam[i]);
+    }
+    __syncthreads();
+    // best component by density and by area (ties: first in raster order)
+    RoiBest dens = {0.0, -1}, big = {0.0, -1};
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        if (lab[i] != i) continue;
+        const double a = (double)ar[i];
+        dens = roi_better(dens, RoiBest{sm[i] / a, i});
+        big = roi_better(big, RoiBest{a, i});
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        RoiBest od, ob;
+        od.key = __shfl_xor_sync(0xffffffffu, dens.key, o);
+        od.idx = __shfl_xor_sync(0xffffffffu, dens.idx, o);
+        ob.key = __shfl_xor_sync(0xffffffffu, big.key, o);
+        ob.idx = __shfl_xor_sync(0xffffffffu, big.idx, o);
+        dens = roi_better(dens, od);
+        big = roi_better(big, ob);
+    }
+    if ((tid & 31) == 0) {
+        s_best[0][tid >> 5] = dens;
+        s_best[1][tid >> 5] = big;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        dens = s_best[0][0];
+        big = s_best[1][0];
+        for (int w = 1; w < kSeedThreads / 32; w++) {
+            dens = roi_better(dens, s_best[0][w]);
+            big = roi_better(big, s_best[1][w]);
+        }
+        int sel = largest_only ? big.idx : dens.idx;
+        // tcam_seeding.py:381-384: a dense but tiny component gives way to the largest one
+        if (!largest_only && sel >= 0 && (double)ar[sel] < min_area) sel = big.idx;
+        s_sel = sel;
+    }
+    __syncthreads();
+    const int sel = s_sel;
+    int x0 = W, y0 = H, x1 = -1, y1 = -1;
+    long long *out = roi + (size_t)b * HW;
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        const bool in = sel >= 0 && lab[i] == sel;
+        out[i] = in ? 1 : 0;
+        if (in) {
+            const int y = i / W, x = i - y * W;
+            x0 = min(x0, x);
+            y0 = min(y0, y);
+            x1 = max(x1, x);
+            y1 = max(y1, y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((tid & 31) == 0) {
+        s_box[0][tid >> 5] = x0;
+        s_box[1][tid >> 5] = y0;
+        s_box[2][tid >> 5] = x1;
+        s_box[3][tid >> 5] = y1;
+    }
+    __syncthreads();
+    x0 = s_box[0][0];
+    y0 = s_box[1][0];
+    x1 = s_box[2][0];
+    y1 = s_box[3][0];
+    for (int w = 1; w < kSeedThreads / 32; w++) {
+        x0 = min(x0, s_box[0][w]);
+        y0 = min(y0, s_box[1][w]);
+        x1 = max(x1, s_box[2][w]);
+        y1 = max(y1, s_box[3][w]);
+    }
+    int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;   // no contour: [[0, 0, 0, 0]] (wsol.py:125-126)
+    if (x1 >= 0) {
+        // cv2.boundingRect: (x, y, w, h) = (min, min, max-min+1, max-min+1); x1 = min(x + w, W - 1) (wsol.py:133-136)
+        bx0 = x0;
+        by0 = y0;
+        bx1 = min(x1 + 1, W - 1);
+        by1 = min(y1 + 1, H - 1);
+    }
+    if (tid == 0) {
+        bbox[b * 4 + 0] = bx0;
+        bbox[b * 4 + 1] = by0;
+        bbox[b * 4 + 2] = bx1;
+        bbox[b * 4 + 3] = by1;
+    }
+    float *mask = bbox_mask + (size_t)b * HW;
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        const int y = i / W, x = i - y * W;
+        mask[i] = (x >= bx0 && x < bx1 && y >= by0 && y < by1) ? 1.0f : 0.0f;   // bbox_mask[y0:y1, x0:x1] = 1
+    }
+}
+
 // torch.nan_to_num(x, nan=0.0, posinf=1.0, neginf=0.0)  (wsol_loader.py:634, train_wsol.py:426,431)
 __device__ __forceinline__ float nan_to_num01(float v)
 {

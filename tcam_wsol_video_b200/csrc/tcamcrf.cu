@@ -2073,6 +2073,36 @@ int tcam_temporal_max(const float *cams_dev, float *out_dev, int B, int T, int H
     return TCAMCRF_OK;
 }
 
+size_t tcam_roi_components_scratch_bytes(int B, int H, int W)
+{
+    if (B < 1 || H < 1 || W < 1) return 0;
+    return (size_t)B * H * W * (2 * sizeof(int) + sizeof(double)) + 256;
+}
+
+int tcam_roi_components(const float *cams_dev, const float *thresh_dev, long long *roi_dev, float *bbox_mask_dev,
+                        int *bbox_dev, int B, int H, int W, int largest_only, float p_min_area, void *scratch_dev,
+                        size_t scratch_bytes, void *cuda_stream)
+{
+    if (!cams_dev || !thresh_dev || !roi_dev || !bbox_mask_dev || !bbox_dev || !scratch_dev)
+        return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || H < 1 || W < 1) return fail(TCAMCRF_ERR_INVALID, "B,H,W must be positive");
+    if ((long long)H * W > (1ll << 26)) return fail(TCAMCRF_ERR_INVALID, "image too large");
+    if (scratch_bytes < tcam_roi_components_scratch_bytes(B, H, W))
+        return fail(TCAMCRF_ERR_WORKSPACE, "scratch too small");
+    const size_t n = (size_t)B * H * W;
+    char *base = (char *)(((uintptr_t)scratch_dev + 255) / 256 * 256);
+    double *sum = (double *)base;
+    int *labels = (int *)(base + n * sizeof(double));
+    int *area = labels + n;
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    // min_area = (h * w) * p_min_area_roi in float64 (tcam_seeding.py:364)
+    roi_components_kernel<<<B, kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(
+        cams_dev, thresh_dev, roi_dev, bbox_mask_dev, bbox_dev, labels, area, sum, H, W, largest_only ? 1 : 0,
+        (double)((long long)H * W) * (double)p_min_area);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
 int tcam_temporal_max_renorm(const float *cams_dev, float *out_dev, int B, int T, int HW, float h, void *cuda_stream)
 {
     if (!cams_dev || !out_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");

@@ -330,5 +330,36 @@ def otsu_roi(cams: torch.Tensor):
     return roi, th
 
 
-__all__ = ["Lattice", "otsu_roi", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "prepare_std_cams", "workspace_status", "release_workspaces",
+def roi_components(cams: torch.Tensor, largest_only: bool, p_min_area: float, thresh: Optional[float] = None):
+    """ROI = one 4-connected component of ``cam*255 >= thresh`` per sample: the densest one ('roi_high_density',
+    falling back to the largest when it covers less than p_min_area of the frame) or the largest ('largest').
+
+    cams [B,1,H,W] or [B,H,W] float32 CUDA; thresh in [0,1] or None (Otsu per sample, like get_thresh).
+    Returns (roi long, same shape as cams; bbox_mask float32 [B,H,W]; bbox float32 [B,4] = x0,y0,x1,y1).
+    GPU version of GetRoiSingleCam.__call__ (dlib/cams/tcam_seeding.py:347-412)."""
+    lib = _lib.load()
+    _require_cuda(cams, "cams")
+    x = cams.detach().float().contiguous()
+    if x.ndim == 4:
+        assert x.shape[1] == 1
+    b, h, w = x.shape[0], x.shape[-2], x.shape[-1]
+    if thresh is None:
+        _, th = otsu_roi(x)
+    else:
+        assert thresh >= 0, thresh
+        th = torch.full((b,), float(thresh) * 255.0, dtype=torch.float32, device=x.device)
+    roi = torch.empty(x.shape, dtype=torch.long, device=x.device)
+    mask = torch.empty((b, h, w), dtype=torch.float32, device=x.device)
+    bbox = torch.empty((b, 4), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        nbytes = lib.tcam_roi_components_scratch_bytes(b, h, w)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.tcam_roi_components(x.data_ptr(), th.data_ptr(), roi.data_ptr(), mask.data_ptr(),
+                                           bbox.data_ptr(), b, h, w, 1 if largest_only else 0, float(p_min_area),
+                                           scratch.data_ptr(), nbytes, _stream_ptr(x.device)),
+                   "tcam_roi_components")
+    return roi, mask, bbox.float()
+
+
+__all__ = ["Lattice", "otsu_roi", "roi_components", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "prepare_std_cams", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

@@ -28,7 +28,7 @@ import torch.nn.functional as F
 
 from . import _lib, ops
 
-__all__ = ['TCAMSeeder', 'SEED_UNIFORM', 'SEED_WEIGHTED']
+__all__ = ['TCAMSeeder', 'GetRoiSingleCam', 'SEED_UNIFORM', 'SEED_WEIGHTED', 'ROI_ALL', 'ROI_H_DENSITY', 'ROI_LARGEST']
 
 # dlib/configure/constants.py:352-354,368-372
 SEED_UNIFORM = 'seed_uniform'
@@ -202,10 +202,10 @@ class TCAMSeeder(nn.Module):
         if self.use_roi:
             if roi is None:
                 # the reference falls back to GetRoiSingleCam on the CPU here (tcam_seeding.py:476-479)
-                if self.roi_method != ROI_ALL:
-                    raise NotImplementedError(f'roi=None with roi_method={self.roi_method!r}: only {ROI_ALL!r} has a '
-                                              'GPU implementation (the others need connected components on the CPU)')
-                roi, _ = ops.otsu_roi(x)
+                if self.roi_method == ROI_ALL:
+                    roi, _ = ops.otsu_roi(x)
+                else:
+                    roi, _, _ = ops.roi_components(x, self.roi_method == ROI_LARGEST, self.p_min_area_roi)
             _roi = self._erode(roi.to(x.device)).long().contiguous()
         return x.detach().float().contiguous(), _roi
 
@@ -249,3 +249,43 @@ class TCAMSeeder(nn.Module):
                f'support_background={self.support_background},' \
                f'multi_label_flag={self.multi_label_flag}, ' \
                f'seg_ignore_idx={self.ignore_idx}, seed_tech={self.seed_tech}'
+
+
+class GetRoiSingleCam(object):
+    """ROI of ONE cam [H,W] (dlib/cams/tcam_seeding.py:316-430) on the GPU: Otsu threshold (or `thresh` in [0,1]),
+    then the whole thresholded map ('roi_all') or one connected component ('roi_high_density', 'largest').
+    Returns (final_roi long [H,W], bbox_mask float [H,W], bbox float [1,4] = x0,y0,x1,y1) on the cam's device
+    (the reference returns CPU tensors).  For a batch use ops.otsu_roi / ops.roi_components directly."""
+
+    def __init__(self, roi_method: str, p_min_area_roi: float):
+        assert roi_method in ROI_SELECT, roi_method
+        self.roi_method = roi_method
+        assert 0 < p_min_area_roi < 1., p_min_area_roi
+        self.p_min_area_roi = p_min_area_roi
+
+    def __call__(self, cam: torch.Tensor, thresh: float = None):
+        assert torch.is_tensor(cam)
+        assert cam.ndim == 2, cam.ndim
+        if not cam.is_cuda:
+            raise _lib.TcamCrfError('GetRoiSingleCam needs a CUDA tensor: this package has no CPU path')
+        h, w = cam.shape
+        x = cam.detach().float().reshape(1, h, w)
+        if self.roi_method == ROI_ALL:
+            if thresh is None:
+                roi, _ = ops.otsu_roi(x)
+            else:
+                assert thresh >= 0, thresh
+                roi = ((x * 255.) >= torch.tensor(thresh * 255., dtype=torch.float32, device=x.device)).long()
+            # "not used" box of the reference: [0, 0, h - 1, w - 1] read back as x0, y0, x1, y1 (tcam_seeding.py:345,408)
+            bbox = torch.tensor([[0, 0, h - 1, w - 1]], dtype=torch.float32, device=x.device)
+            mask = torch.zeros((h, w), dtype=torch.float32, device=x.device)
+            mask[0:w - 1, 0:h - 1] = 1.
+            return roi[0], mask, bbox
+        roi, mask, bbox = ops.roi_components(x, self.roi_method == ROI_LARGEST, self.p_min_area_roi, thresh)
+        return roi[0], mask[0], bbox.reshape(1, 4)
+
+    @staticmethod
+    def get_thresh(cam: torch.Tensor) -> float:
+        """Otsu threshold on floor(cam*255), 0 for a flat cam (tcam_seeding.py:419-430); in [0, 255]."""
+        _, th = ops.otsu_roi(cam.detach().float().reshape(1, *cam.shape[-2:]))
+        return float(th.item())

@@ -120,8 +120,7 @@ def test_seeder_api_surface(torch_cuda):
     cam, roi = _make(torch, 2, 32, 32, seed=1)
     out = mod.use_all_roi(cam, roi)
     assert torch.equal(out == 1, roi.squeeze(1) == 1) and ((out == 1) | (out == -255)).all()
-    with pytest.raises(NotImplementedError):
-        _seeder(roi_method="largest")(x=cam, roi=None)
+    assert _seeder(roi_method="largest")(x=cam, roi=None).shape == (2, 32, 32)   # component roi computed on the GPU
     # erosion of the roi before sampling (fg_erode_iter > 0) keeps seeds inside the eroded region
     mod = _seeder(fg_erode_k=5, fg_erode_iter=1, ksz=1, max_=8)
     seeds = mod(x=cam, roi=roi)
@@ -216,3 +215,53 @@ def test_prepare_std_cams_disq(torch_cuda, size):
     assert torch.isfinite(got).all()
     assert (got - want_gpu).abs().max().item() <= 1e-6
     assert (got - want_cpu).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("method", ["roi_high_density", "largest"])
+@pytest.mark.parametrize("shape", [(224, 224), (37, 61), (8, 5)])
+def test_roi_connected_components(torch_cuda, method, shape):
+    """GetRoiSingleCam 'roi_high_density' / 'largest' on the GPU (union-find components, per-component density and
+    area, bounding box) against the line-by-line restatement (oracle/seeding.py; scipy.ndimage.label for
+    skimage.measure.label, bounding rectangle for the cv2 contour).  Masks, boxes and box masks must be identical."""
+    torch = torch_cuda
+    from oracle import seeding as oseed
+    from tcam_wsol_video_b200 import ops
+    from tcam_wsol_video_b200.tcam_seeding import GetRoiSingleCam
+    h, w = shape
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    low = torch.rand((6, 1, 7, 7), generator=g)
+    cams = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)[:, 0]
+    cams = cams + 0.05 * torch.rand((6, h, w), generator=g)                     # several blobs per map
+    cams[4] = 0.3                                                                # flat: threshold 0, everything in
+    cams[5] = torch.rand((h, w), generator=g)                                    # salt and pepper: many components
+    for p_min in (0.05, 0.6):
+        roi, mask, bbox = ops.roi_components(cams.cuda(), method == "largest", p_min)
+        for i in range(cams.shape[0]):
+            want_roi, want_mask, want_bbox = oseed.roi_components_single_cam(cams[i].numpy(), method, p_min)
+            assert np.array_equal(roi[i].cpu().numpy(), want_roi), (i, p_min)
+            assert np.array_equal(bbox[i].cpu().numpy().reshape(1, 4), want_bbox), (i, p_min)
+            assert np.array_equal(mask[i].cpu().numpy(), want_mask), (i, p_min)
+    # fixed threshold (the loader passes roi_thresholds when it has them) and the single-cam class
+    getter = GetRoiSingleCam(roi_method=method, p_min_area_roi=0.05)
+    r1, m1, b1 = getter(cams[1].cuda(), thresh=0.5)
+    w1 = oseed.roi_components_single_cam(cams[1].numpy(), method, 0.05, thresh=0.5)
+    assert np.array_equal(r1.cpu().numpy(), w1[0]) and np.array_equal(m1.cpu().numpy(), w1[1])
+    assert np.array_equal(b1.cpu().numpy(), w1[2]) and r1.dtype == torch.long
+    # nothing above the threshold: empty roi, box [0,0,0,0]
+    r0, m0, b0 = getter(torch.zeros(h, w).cuda(), thresh=0.5)
+    assert r0.sum().item() == 0 and m0.sum().item() == 0 and b0.abs().sum().item() == 0
+
+
+def test_seeder_computes_component_roi_when_none_is_given(torch_cuda):
+    """TCAMSeeder(roi_method='largest') with roi=None: the reference calls GetRoiSingleCam on the CPU per sample
+    (tcam_seeding.py:476-479); here the batched kernel.  Same seeds as passing that roi explicitly."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    cam, _ = _make(torch, 4, 64, 64, seed=21)
+    seeder = _seeder(roi_method="largest")
+    roi, _, _ = ops.roi_components(cam, True, 0.05)
+    torch.manual_seed(5)
+    a = seeder(cam, None)
+    torch.manual_seed(5)
+    b = seeder(cam, roi)
+    assert torch.equal(a, b)
