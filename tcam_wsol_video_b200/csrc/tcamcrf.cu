@@ -904,6 +904,40 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(const BlurParams p, int 
     }
 }
 
+// The last block to arrive folds the block partials of seg . AS (fixed order => deterministic given AS) into the
+// running total and, when p.loss_out is set (last chunk), writes the loss: no separate reduction launches.
+// Call with all threads of the block, after the block's partial has been written.
+__device__ __forceinline__ void fold_loss_partials(const PixelParams &p)
+{
+    __shared__ bool s_last;
+    __shared__ double s_sum[kThreads / 32];
+    const int nblocks = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.ctrl + kCtrlTicket, 1) == nblocks - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += kThreads) sum += (double)__ldcg(p.partial + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = p.acc[0];
+        for (int w = 0; w < kThreads / 32; w++) total += s_sum[w];
+        p.acc[0] = total;
+        p.ctrl[kCtrlTicket] = 0;
+        if (p.loss_out) {
+            // loss = -(sum)/n_norm, NaN when the device status is set (dense_crf_loss.py:63-64)
+            const float s = (float)total;
+            p.loss_out[0] = p.ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(-s, p.n_norm);
+        }
+    }
+}
+
 template <int D, int V, bool L>
 __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
 {
@@ -971,35 +1005,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
         if (threadIdx.x == 0 && p.partial) p.partial[(size_t)n * gridDim.x + blockIdx.x] = t;
     }
     if (!p.partial) return;
-    // The last block to arrive folds the partial sums (fixed order => deterministic given AS) into the
-    // running total and, on the last chunk, writes the loss: no separate reduction launches.
-    __shared__ bool s_last;
-    __shared__ double s_sum[kThreads / 32];
-    const int nblocks = gridDim.x * gridDim.y;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(p.ctrl + kCtrlTicket, 1) == nblocks - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double sum = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += kThreads) sum += (double)__ldcg(p.partial + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double total = p.acc[0];
-        for (int w = 0; w < kThreads / 32; w++) total += s_sum[w];
-        p.acc[0] = total;
-        p.ctrl[kCtrlTicket] = 0;
-        if (p.loss_out) {
-            // loss = -(sum)/n_norm, NaN when the device status is set (dense_crf_loss.py:63-64)
-            const float s = (float)total;
-            p.loss_out[0] = p.ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(-s, p.n_norm);
-        }
-    }
+    fold_loss_partials(p);
 }
 
 // grad = ((-2*g) * AS) / n  with the reference's rounding order (dense_crf_loss.py:73)
