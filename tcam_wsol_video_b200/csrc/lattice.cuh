@@ -254,7 +254,24 @@ struct TableGeom {
     unsigned int slots1, slots2;  // powers of two, 2^8 .. 2^30
     unsigned int window;          // max probes in the primary tier
     unsigned int shift1, shift2;  // 32 - log2(slots): hash_slot() keeps the top log2(slots) bits
+    unsigned int base2;           // where the overflow tier starts inside a frame's table (the allocated size of
+                                  // the primary tier; slots1 may be smaller: see effective_geom)
 };
+
+// The part of the primary tier a call really uses.  The allocation (base2 entries) is sized for iid-noise frames,
+// ~1.1 vertices per pixel; real frames produce 10-20 times fewer, and clearing + probing a table of that size is
+// pure overhead for them.  prepare_kernel therefore picks slots1 = the power of two >= 4 x the largest per-frame
+// vertex count of the PREVIOUS call on this workspace (never above the allocation, and the allocation itself on
+// first use or after a call that spilled into the overflow tier), and the kernels of the call read it back from the
+// workspace.  A guess that turns out too small costs speed only: the window fills up and keys go to the overflow
+// tier, which is sized for the worst case.  The result never depends on the size.
+__device__ __forceinline__ TableGeom effective_geom(TableGeom g, unsigned int eff_slots1)
+{
+    g.slots1 = eff_slots1;
+    g.shift1 = 1u + (unsigned int)__clz((int)eff_slots1);   // 32 - log2(eff) for a power of two
+    g.window = eff_slots1 < g.window ? eff_slots1 : g.window;
+    return g;
+}
 __device__ __forceinline__ unsigned int hash_primary(unsigned long long k, const TableGeom &g)
 {
     return hash_slot(k, kHashMul1, g.shift1);
@@ -296,19 +313,19 @@ __device__ __forceinline__ int table_insert_from(Entry *tab, const TableGeom g, 
         cur = load_key_cg(tab + h);
     }
     spilled = true;
-    Entry *ov = tab + g.slots1;
+    Entry *ov = tab + g.base2;
     const unsigned int mask2 = g.slots2 - 1;
     h = hash_overflow(key, g);
     for (probes = 0; probes <= mask2; probes++) {
         cur = load_key_cg(ov + h);
-        if (cur == key) return (int)(g.slots1 + h);
+        if (cur == key) return (int)(g.base2 + h);
         if (cur == kEmptyKey) {
             cur = atomicCAS(&ov[h].key, kEmptyKey, key);
             if (cur == kEmptyKey) {
                 won = true;
-                return (int)(g.slots1 + h);
+                return (int)(g.base2 + h);
             }
-            if (cur == key) return (int)(g.slots1 + h);
+            if (cur == key) return (int)(g.base2 + h);
         }
         h = (h + 1) & mask2;
     }
@@ -329,7 +346,7 @@ __device__ __forceinline__ int table_lookup_from(const Entry *__restrict__ tab, 
         h = (h + 1) & mask1;
         e = __ldg(reinterpret_cast<const uint4 *>(tab + h));
     }
-    const Entry *ov = tab + g.slots1;
+    const Entry *ov = tab + g.base2;
     const unsigned int mask2 = g.slots2 - 1;
     h = hash_overflow(key, g);
     for (probes = 0; probes <= mask2; probes++) {

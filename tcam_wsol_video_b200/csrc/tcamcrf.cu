@@ -149,6 +149,8 @@ constexpr int kCtrlAccInts = 8;      // a double: running sum of seg . AS over t
 constexpr int kCtrlResetInts = 16;
 constexpr int kCtrlMagic = 16;      // signature of the plan that last initialised the tables
 constexpr int kCtrlDirty = 17;      // overflow tier holds keys (must be cleared before reuse)
+constexpr int kCtrlEffSlots = 18;   // primary-tier size in use by the current call (effective_geom)
+constexpr int kCtrlPrevMax = 19;    // largest per-frame vertex count of the last build on this workspace
 constexpr int kCtrlCounts = 32;     // [chunk] vertices per frame
 
 struct Plan {
@@ -219,6 +221,7 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     auto log2u = [](unsigned int v) { int l = 0; while ((1u << l) < v) l++; return (unsigned int)l; };
     pl.geom.shift1 = 32 - log2u(pl.geom.slots1);
     pl.geom.shift2 = 32 - log2u(pl.geom.slots2);
+    pl.geom.base2 = pl.geom.slots1;
     pl.slots = pl.geom.slots1 + pl.geom.slots2;
     float pf = cfg->pool_factor > 0.f ? cfg->pool_factor : 1.0f;
     if (pf > 1.f) pf = 1.f;
@@ -314,6 +317,9 @@ __device__ __forceinline__ float load_pixel<uint8_t>(const void *base, size_t id
     return (float)__ldg((const uint8_t *)base + idx);
 }
 
+#ifndef TCAMCRF_ADAPTIVE_TABLE
+#define TCAMCRF_ADAPTIVE_TABLE 1
+#endif
 // Clears the tables of `nc` frames: always the primary tier, the overflow tier only when the workspace is
 // new (magic mismatch) or the previous use spilled into it.  Also zeroes the per-frame vertex counters.
 __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int frame0, int nc, int chunk,
@@ -323,7 +329,21 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
     pdl_launch_dependents();
     // frame0 > 0: a later section of a chunk whose first section has already dealt with the overflow tiers
     const bool full = frame0 == 0 && ((ctrl[kCtrlMagic] != sig) || (ctrl[kCtrlDirty] != 0));
-    const unsigned int slots = geom.slots1 + geom.slots2;
+    // primary-tier size for this call (see effective_geom); later sections of a chunk take the first one's
+    unsigned int eff = geom.slots1;
+#if TCAMCRF_ADAPTIVE_TABLE
+    if (frame0 > 0) {
+        eff = (unsigned int)ctrl[kCtrlEffSlots];
+    } else if (!full) {
+        const unsigned int want = 4u * (unsigned int)ctrl[kCtrlPrevMax];
+        unsigned int e = geom.slots1 >> 4;   // floor: bounds what a bad guess costs (window-long probe chains)
+        if (e < 4096u) e = 4096u;
+        while (e < want && e < geom.slots1) e <<= 1;
+        eff = e < geom.slots1 ? e : geom.slots1;
+    }
+#endif
+    const unsigned int slots = geom.base2 + geom.slots2;
+    geom.slots1 = eff;
     const long long n_primary = (long long)nc * geom.slots1;
     // the overflow tiers of ALL frames of the workspace are cleared together: the dirty flag is per workspace
     const long long total = n_primary + (full ? (long long)chunk * geom.slots2 : 0);
@@ -340,12 +360,15 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
         } else {
             const long long o = i - n_primary;
             n = o / geom.slots2;
-            s = geom.slots1 + (o - n * geom.slots2);
+            s = geom.base2 + (o - n * geom.slots2);
         }
         t4[n * slots + s] = empty;
     }
     if (tid < nc) ctrl[kCtrlCounts + frame0 + tid] = 0;
-    if (tid == 0 && frame0 == 0) ctrl[kCtrlLastCount] = 0;
+    if (tid == 0 && frame0 == 0) {
+        ctrl[kCtrlLastCount] = 0;
+        ctrl[kCtrlEffSlots] = (int)eff;
+    }
 }
 
 // Occupancy target of the build kernel: 5 blocks of 256 threads per SM caps it at 48 registers (a few
@@ -418,6 +441,8 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     pdl_wait();
     pdl_launch_dependents();
     if (!ok) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_KEY_RANGE);
+    // the primary-tier size this call works with (chosen by prepare_kernel)
+    const TableGeom geom = effective_geom(p.geom, (unsigned int)p.ctrl[kCtrlEffSlots]);
 
     // Warp-cooperative insertion.  A warp holds 32 neighbouring pixels of one image row; in real frames
     // most of them fall on the same lattice vertices.  Lanes whose key equals their left neighbour's form a
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     // for all the keys it leads in lock step: every round issues one load per pending key before any result
     // is consumed, so the d+1 dependent probe chains overlap instead of running one after the other.
     Entry *tab = p.table + (size_t)n * p.slots;
-    const unsigned int mask1 = p.geom.slots1 - 1;
+    const unsigned int mask1 = geom.slots1 - 1;
     unsigned int pend = 0;
     int leader[D + 1];
     unsigned int hh[D + 1];
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
         slot[r] = -1;
         if (active && head) {
             pend |= 1u << r;
-            hh[r] = hash_primary(key[r], p.geom);
+            hh[r] = hash_primary(key[r], geom);
             cur[r] = load_key_cg(tab + hh[r]);
         }
     }
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     for (int r = 0; r <= D; r++) {
         if (pend & (1u << r)) {  // stragglers: long probe chains, overflow tier
             bool won, spilled;
-            slot[r] = table_insert_from(tab, p.geom, key[r], hh[r], (unsigned int)rounds, cur[r], won, spilled);
+            slot[r] = table_insert_from(tab, geom, key[r], hh[r], (unsigned int)rounds, cur[r], won, spilled);
             if (won) wonmask |= 1u << r;
             if (slot[r] < 0) table_full = true;
             spilled_any |= spilled;
@@ -633,7 +658,7 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
     const int total = load_frame_prefix(p.ctrl, p.frame0, nc, p.stride, s_prefix);
     const int stride = gridDim.x * kThreads;
     const int tid = blockIdx.x * kThreads + threadIdx.x;
-    const unsigned int mask1 = p.geom.slots1 - 1;
+    const TableGeom geom = effective_geom(p.geom, (unsigned int)p.ctrl[kCtrlEffSlots]);
     const int work = total * (D + 1);   // < 2^31: pool * (D+1) is checked in make_plan
     // items are ordered frame by frame (so the grid probes one or two frame tables at a time and they stay
     // in L2), axis-major inside a frame: adjacent lanes handle adjacent vertices of one axis (coalesced key
@@ -652,8 +677,8 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         // both neighbours are looked up (their first probes are issued together) and the link pair is written
         // with one coalesced 8-byte store: no scattered 4-byte store into another vertex' links, and no
         // "missing" preset pass over the link table
-        const unsigned int h1 = hash_primary(k1, p.geom);
-        const unsigned int h2 = hash_primary(k2, p.geom);
+        const unsigned int h1 = hash_primary(k1, geom);
+        const unsigned int h2 = hash_primary(k2, geom);
         const uint4 e1 = __ldg(reinterpret_cast<const uint4 *>(tab + h1));
         const uint4 e2 = __ldg(reinterpret_cast<const uint4 *>(tab + h2));
         if (p.zero_values && axis == 0) {   // the value row of this vertex, cleared for the splat
@@ -664,8 +689,8 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
                 for (int q = 0; q < p.Kp; q++) p.values[(size_t)id * p.Kp + q] = 0.f;
             }
         }
-        const int nb1 = table_lookup_from(tab, p.geom, k1, h1, 0, e1);
-        const int nb2 = table_lookup_from(tab, p.geom, k2, h2, 0, e2);
+        const int nb1 = table_lookup_from(tab, geom, k1, h1, 0, e1);
+        const int nb2 = table_lookup_from(tab, geom, k2, h2, 0, e2);
         p.nbr[(size_t)axis * p.pool + id] = make_int2(nb1, nb2);
     }
     if (tid == 0) {
@@ -675,6 +700,10 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(const VertexParams 
         p.ctrl[kCtrlDirty] = (p.frame0 == 0 ? 0 : p.ctrl[kCtrlDirty]) | p.ctrl[kCtrlDirtyNew];
         p.ctrl[kCtrlDirtyNew] = 0;
         p.ctrl[kCtrlMagic] = p.sig;
+        // the next call sizes its primary tier from this (effective_geom)
+        int mx = p.frame0 == 0 ? 0 : p.ctrl[kCtrlPrevMax];
+        for (int f = 0; f < nc; f++) mx = max(mx, s_prefix[f + 1] - s_prefix[f]);
+        p.ctrl[kCtrlPrevMax] = mx;
     }
 }
 

@@ -363,6 +363,30 @@ def test_overflow_tier_is_cleared_between_calls(torch_cuda, oracle_mod):
         assert m_total == m_want
 
 
+def test_adaptive_table_size_follows_the_frames(torch_cuda, oracle_mod):
+    """The primary table tier a call uses is sized from the previous call's vertex counts (effective_geom).  Alternate
+    natural frames (few vertices) and iid-noise frames (the worst case) on ONE workspace, both ways round: a guess
+    that is too small must only cost speed (overflow tier), never correctness."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import _lib, ops
+    n, k, h, w = 3, 2, 96, 112
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    seg_np = synth.make_segs(n, k, h, w, seed=3)
+    seg = torch.from_numpy(seg_np).cuda()
+    sizes = []
+    for step, kind in enumerate(["natural", "natural", "noise", "noise", "natural", "noise", "natural"]):
+        img = synth.make_images(n, h, w, kind, seed=40 + step)
+        got, _, ws = ops.crf_forward(torch.from_numpy(img), seg, cfg, want_loss=False, check=True)
+        want = oracle_mod.port_bilateralfilter_batch(img, seg_np, n, k, h, w, 15.0, 100.0).reshape(seg_np.shape)
+        _assert_close(got.cpu().numpy(), want, f"AS, call {step} ({kind})")
+        sizes.append(int(ws.view(torch.int32)[(ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr():][18].item())
+                     if ws.data_ptr() % 256 == 0 else None)
+    # the size in use shrinks after a natural call and grows back after a noise call (word 18 of the ctrl block)
+    if all(s is not None for s in sizes):
+        assert sizes[1] < sizes[3], sizes
+        assert sizes[4] == sizes[3] and sizes[5] < sizes[3], sizes     # call 4 still sized by the noise call 3
+
+
 def test_full_size_properties_config2(torch_cuda):
     """BASELINE configs[1] at full size (32 x 10 classes x 224^2): too slow for the scalar oracle in a unit
     test, so check size-independent properties: linearity, channel independence (K=10 in one pass equals
