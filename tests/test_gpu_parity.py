@@ -363,13 +363,14 @@ def test_overflow_tier_is_cleared_between_calls(torch_cuda, oracle_mod):
         assert m_total == m_want
 
 
-def test_adaptive_table_size_follows_the_frames(torch_cuda, oracle_mod):
+@pytest.mark.parametrize("k", [2, 10, 7])
+def test_adaptive_table_size_follows_the_frames(torch_cuda, oracle_mod, k):
     """The primary table tier a call uses is sized from the previous call's vertex counts (effective_geom).  Alternate
     natural frames (few vertices) and iid-noise frames (the worst case) on ONE workspace, both ways round: a guess
     that is too small must only cost speed (overflow tier), never correctness."""
     torch = torch_cuda
     from tcam_wsol_video_b200 import _lib, ops
-    n, k, h, w = 3, 2, 96, 112
+    n, h, w = 3, 96, 112
     cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
     seg_np = synth.make_segs(n, k, h, w, seed=3)
     seg = torch.from_numpy(seg_np).cuda()
