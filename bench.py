@@ -330,6 +330,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "tcamcrf_loss_fwd_bwd_host (host pointers in, loss + gradient out)"}
 
+        # context, not the headline: the call the reference's trainer makes (dlib/losses/tcam.py:113-115) -- frames
+        # from pinned host memory (train_wsol.py:1128 keeps raw_img on the CPU), segmentations where the network
+        # left them (device), loss read back; the gradient stays on the device for the backbone's backward pass
+        def module_step(i):
+            img_h, _, _, seg_d = sets[i % len(sets)]
+            seg_d.grad = None
+            loss = crf(images=img_h, segmentations=seg_d)
+            loss.backward()
+            return loss.item()
+
+        for i in range(3):
+            module_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            module_step(i)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        t = torch.tensor([dtm], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dtm = float(t.item())
+        e2e["trainer_call"] = {"value": world * N * e2e_steps / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm / e2e_steps,
+                               "h2d_bytes_per_step": int(4 * N * 3 * P), "d2h_bytes_per_step": 4,
+                               "api": "DenseCRFLoss(images=pinned host float32, segmentations=device).backward(); "
+                                      "loss.item()"}
+
     # ---- the same step on the other input regimes (short, device-resident; context for the headline number)
     extra = {}
     if world == 1 and not args.no_extra:
