@@ -465,3 +465,25 @@ def test_temporal_max_bit_exact(torch_cuda):
     assert got.shape == want.shape
     assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
     assert torch.equal(torch.isnan(got), torch.isnan(want))
+
+
+@pytest.mark.parametrize("case", ["k21_voc", "wide_clip_colour", "tall_512", "k1", "k33"])
+def test_unusual_shapes(torch_cuda, oracle_mod, case):
+    """Shapes away from the benchmark: 21 classes (run-time columns-per-row in the blur), a width-concatenated clip
+    through the colour lattice (RgbJointConRanFieldTcams' [H, T*W] layout), a 512 x 384 frame, one class, 33 classes
+    (nine float4 columns)."""
+    from tcam_wsol_video_b200 import _lib, ops
+    torch = torch_cuda
+    n, k, h, w, color = {"k21_voc": (2, 21, 60, 70, False), "wide_clip_colour": (2, 2, 56, 5 * 56, True),
+                         "tall_512": (1, 2, 512, 384, False), "k1": (3, 1, 33, 47, False),
+                         "k33": (1, 33, 24, 31, False)}[case]
+    img = synth.make_images(n, h, w, "natural" if case != "k33" else "noise", seed=len(case))
+    seg = synth.make_segs(n, k, h, w, seed=len(case))
+    if color:
+        cfg = _lib.make_config(_lib.FEAT_COLOR, 3, 15.0)
+        want = oracle_mod.port_colorbilateralfilter_batch(img, seg, n, k, h, w, 15.0, 3)
+    else:
+        cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+        want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0)
+    got, _, _ = ops.crf_forward(torch.from_numpy(img), torch.from_numpy(seg).cuda(), cfg, want_loss=False, check=True)
+    _assert_close(got.cpu().numpy(), want.reshape(seg.shape), case)
