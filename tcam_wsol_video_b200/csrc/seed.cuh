@@ -249,6 +249,172 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_kernel(const SeedPar
     }
 }
 
+// inverse of float_order_key
+__device__ __forceinline__ float float_from_order_key(unsigned int u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// The same selection with the sample's keys resident in shared memory (HW * 4 bytes of dynamic shared memory, i.e.
+// frames up to ~56 k pixels: 224 x 224 fits): the temporal max is taken once instead of in each of the four radix
+// passes and in the ranking pass, and the row-major candidate ranks come from TWO block scans over per-thread
+// counts -- every thread owns a contiguous chunk of pixels -- instead of two scans per 1024 pixels (~100 scans,
+// ~300 barriers at 224 x 224).  Bit-identical results to seed_select_kernel; TCAMSeeder.forward_stack on 32 samples of
+// 224 x 224: 0.48 -> 0.30 ms (tools/seed_timing.py).
+__global__ void __launch_bounds__(kSeedThreads) seed_select_smem_kernel(const SeedParams p)
+{
+    extern __shared__ unsigned int s_key[];   // [HW] selection keys, later the scores
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[33];
+    __shared__ unsigned int s_prefix;
+    __shared__ int s_need;
+    __shared__ float s_best_v[32];
+    __shared__ int s_best_i[32];
+
+    const int b = blockIdx.y;
+    const bool fg = blockIdx.x == 0;
+    const int tid = threadIdx.x;
+    const int HW = p.HW;
+    const float *cam0 = p.cams + (size_t)b * p.T * HW;
+    float *cmax = p.cam_max + (size_t)b * HW;
+    const long long *roi = (fg && p.roi) ? p.roi + (size_t)b * HW : nullptr;
+    int *sel = p.sel + ((size_t)b * 2 + (fg ? 0 : 1)) * p.kmax;
+    const int n = p.n_cand[b * 2 + (fg ? 0 : 1)];
+    int k = fg ? p.k_fg : p.k_bg;
+    if (k > n) k = n;
+    if (k > p.kmax) k = p.kmax;
+    const bool active = n > 0 && k > 0;
+
+    // one pass over the T planes: temporal max (written by the foreground block), value = cam*roi + 1e-8 or
+    // cam + 1e-8 (tcam_seeding.py:511-517,564-565), key = its order key (complemented for the foreground: the n
+    // SMALLEST keys are the candidates)
+    for (int i = tid; i < HW; i += kSeedThreads) {
+        float m = __ldg(cam0 + i);
+        for (int t = 1; t < p.T; t++) {
+            const float v = __ldg(cam0 + (size_t)t * HW + i);
+            m = (m != m) ? m : ((v != v) ? v : (v > m ? v : m));   // torch.maximum: NaN if either is NaN
+        }
+        if (fg) cmax[i] = m;
+        if (roi) m = __fmul_rn(m, (float)__ldg(roi + i));
+        const unsigned int u = float_order_key(__fadd_rn(m, 1e-8f));
+        s_key[i] = fg ? ~u : u;
+    }
+    for (int i = tid; i < p.kmax; i += kSeedThreads) sel[i] = -1;
+    if (!active) return;
+    __syncthreads();
+
+    // radix select, 8 bits at a time from the top: after 4 passes `prefix` is the n-th smallest key
+    unsigned int prefix = 0;
+    int need = n;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += kSeedThreads) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned int himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < HW; i += kSeedThreads) {
+            const unsigned int key = s_key[i];
+            if ((key & himask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0, bin = 0;
+            for (; bin < 256; bin++) {
+                if (run + s_hist[bin] >= need) break;
+                run += s_hist[bin];
+            }
+            s_prefix = prefix | ((unsigned int)bin << shift);
+            s_need = need - run;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        need = s_need;
+        __syncthreads();
+    }
+    const unsigned int kth = prefix;   // keys < kth are candidates; of the keys == kth the first `need` by index
+
+    // row-major ranks: thread t owns pixels [t*chunk, (t+1)*chunk)
+    const int chunk = (HW + kSeedThreads - 1) / kSeedThreads;
+    const int lo = min(tid * chunk, HW), hi = min(lo + chunk, HW);
+    int my_ties = 0;
+    for (int i = lo; i < hi; i++) my_ties += s_key[i] == kth;
+    int tie_total;
+    int tie_rank = block_exclusive_scan(my_ties, s_warp, tie_total);
+    int my_cands = 0;
+    {
+        int tr = tie_rank;
+        for (int i = lo; i < hi; i++) {
+            const unsigned int key = s_key[i];
+            if (key < kth) my_cands++;
+            else if (key == kth) my_cands += (tr++ < need);
+        }
+    }
+    int cand_total;
+    int cand_rank = block_exclusive_scan(my_cands, s_warp, cand_total);
+    // candidates -> their draw q[rank]; score = p / q (torch.multinomial without replacement); others -inf.
+    // The scores replace the keys in shared memory.
+    const float *q = p.q + p.q_offset[b * 2 + (fg ? 0 : 1)];
+    const bool weighted = fg && p.weighted_fg;
+    for (int i = lo; i < hi; i++) {
+        const unsigned int key = s_key[i];
+        bool is_cand = key < kth;
+        if (key == kth) is_cand = tie_rank++ < need;
+        float sc = -INFINITY;
+        if (is_cand) {
+            const float val = float_from_order_key(fg ? ~key : key);
+            sc = __fdiv_rn(weighted ? val : 1.0f, __ldg(q + cand_rank));
+            cand_rank++;
+        }
+        s_key[i] = __float_as_uint(sc);
+    }
+    __syncthreads();
+
+    // k rounds of block argmax (lowest index wins ties); a selected pixel is retired with -inf
+    for (int round = 0; round < k; round++) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < HW; i += kSeedThreads) {
+            const float sc = __uint_as_float(s_key[i]);
+            if (sc > bv || (sc == bv && i < bi && sc != -INFINITY)) {
+                bv = sc;
+                bi = i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if ((tid & 31) == 0) {
+            s_best_v[tid >> 5] = bv;
+            s_best_i[tid >> 5] = bi;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            bv = s_best_v[tid];
+            bi = s_best_i[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            if (tid == 0) {
+                if (bv > -INFINITY && bi < HW) {
+                    sel[round] = bi;
+                    s_key[bi] = __float_as_uint(-INFINITY);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // out[b][y][x] = 1 if a fg seed dilates onto the pixel, 0 if a bg seed does, ignore if none or both
 __global__ void __launch_bounds__(256) seed_labels_kernel(const int *__restrict__ sel, int kmax, int B, int H, int W,
                                                           int ksz, long long ignore_idx, long long *__restrict__ out)

@@ -48,6 +48,10 @@
 #include "lattice.cuh"
 #include "seed.cuh"
 
+#ifndef TCAMCRF_SEED_SMEM
+#define TCAMCRF_SEED_SMEM 1
+#endif
+
 namespace tcamcrf {
 
 // ---------------------------------------------------------------------------
@@ -2057,7 +2061,26 @@ int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const
     sp.weighted_fg = weighted_fg;
     {
         StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
-        seed_select_kernel<<<dim3(2, B), kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(sp);
+        // keys of a sample in shared memory when the frame fits (4 bytes per pixel of the 227 KB an SM has)
+        const size_t smem = (size_t)HW * sizeof(unsigned int);
+        static int smem_limit = -1;   // 0: the opt-in was refused
+        if (smem_limit < 0) {
+            int dev = 0, optin = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            optin -= 2048;   // the kernel's static shared memory
+            if (optin > 0 && cudaFuncSetAttribute(seed_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  optin) == cudaSuccess)
+                smem_limit = optin;
+            else {
+                cudaGetLastError();
+                smem_limit = 0;
+            }
+        }
+        if (TCAMCRF_SEED_SMEM && smem <= (size_t)smem_limit)
+            seed_select_smem_kernel<<<dim3(2, B), kSeedThreads, smem, (cudaStream_t)cuda_stream>>>(sp);
+        else
+            seed_select_kernel<<<dim3(2, B), kSeedThreads, 0, (cudaStream_t)cuda_stream>>>(sp);
     }
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;
