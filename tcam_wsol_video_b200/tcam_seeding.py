@@ -140,6 +140,24 @@ class TCAMSeeder(nn.Module):
             counts[i, 1] = n_bg if self.min_ > 0 else 0
         return counts, stats
 
+    def _candidate_counts_device(self, x: torch.Tensor, roi: Optional[torch.Tensor]) -> torch.Tensor:
+        """The same counts as _candidate_counts, as an int32 [B,2] tensor that never leaves the GPU (no host sync).
+        Only usable when the draws need not line up with the reference's random stream (rng_parity=False)."""
+        b, _, h, w = x.shape
+        flat = x.reshape(b, -1)
+        alive = flat.amin(dim=1) != flat.amax(dim=1)                     # tcam_seeding.py:465
+        if roi is not None:
+            # int(max_p * roi.sum()): float32 product, truncated (tcam_seeding.py:510,519)
+            n_fg = (roi.reshape(b, -1).sum(dim=1).float() * float(np.float32(self.max_p))).to(torch.int32)
+        else:
+            n_fg = torch.full((b,), int(self.max_p * (h * w)), dtype=torch.int32, device=x.device)
+        n_bg = torch.full((b,), int(self.min_p * h * w), dtype=torch.int32, device=x.device)
+        if self.max_ <= 0:
+            n_fg = torch.zeros_like(n_fg)
+        if self.min_ <= 0:
+            n_bg = torch.zeros_like(n_bg)
+        return (torch.stack([n_fg, n_bg], dim=1) * alive.to(torch.int32).unsqueeze(1)).contiguous()
+
     def _draws(self, counts: np.ndarray, device: torch.device) -> Tuple[torch.Tensor, np.ndarray]:
         offsets = np.zeros_like(counts)
         total = 0
@@ -161,15 +179,22 @@ class TCAMSeeder(nn.Module):
             q.exponential_(1)
         return q, offsets
 
-    def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts: np.ndarray):
-        """cams [B,T,H,W] float32 CUDA -> (labels [B,H,W] long, cam_max [B,H,W])."""
+    def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts):
+        """cams [B,T,H,W] float32 CUDA -> (labels [B,H,W] long, cam_max [B,H,W]).  counts: numpy [B,2] (draws sized and
+        ordered like the reference's multinomial calls) or an int32 CUDA tensor [B,2] (no host round trip: every
+        (sample, fg|bg) gets a fixed slot of H*W draws)."""
         lib = _lib.load()
         b, t, h, w = cams.shape
         device = cams.device
-        q, offsets = self._draws(counts, device)
         kmax = max(self.max_, self.min_, 1)
-        meta = torch.from_numpy(np.concatenate([offsets.reshape(-1), counts.reshape(-1)]).astype(np.int32)).to(device)
-        q_off, n_cand = meta[: 2 * b], meta[2 * b:]
+        if torch.is_tensor(counts):
+            q = torch.empty(b * 2 * h * w, dtype=torch.float32, device=device).exponential_(1)
+            q_off = torch.arange(2 * b, dtype=torch.int32, device=device) * (h * w)
+            n_cand = counts.reshape(-1)
+        else:
+            q, offsets = self._draws(counts, device)
+            meta = torch.from_numpy(np.concatenate([offsets.reshape(-1), counts.reshape(-1)]).astype(np.int32)).to(device)
+            q_off, n_cand = meta[: 2 * b], meta[2 * b:]
         cam_max = torch.empty((b, h, w), dtype=torch.float32, device=device)
         scratch = torch.empty((b, 2, h * w), dtype=torch.float32, device=device)
         sel = torch.empty((b, 2, kmax), dtype=torch.int32, device=device)
@@ -214,7 +239,7 @@ class TCAMSeeder(nn.Module):
         x, _roi = self._prep(x, roi)
         b, d, h, w = x.shape
         assert d == 1, d  # todo multilabel.
-        counts, _ = self._candidate_counts(x, _roi)
+        counts = self._candidate_counts(x, _roi)[0] if self.rng_parity else self._candidate_counts_device(x, _roi)
         out, _ = self._select(x, _roi, counts)
         return out.detach()
 
@@ -225,7 +250,8 @@ class TCAMSeeder(nn.Module):
         assert cams.ndim == 4
         x_max = ops.temporal_cam_max(cams.detach().float().contiguous()).unsqueeze(1)   # for the counts only
         x_max, _roi = self._prep(x_max, roi)
-        counts, _ = self._candidate_counts(x_max, _roi)
+        counts = (self._candidate_counts(x_max, _roi)[0] if self.rng_parity
+                  else self._candidate_counts_device(x_max, _roi))
         out, cam_max = self._select(cams.detach().float().contiguous(), _roi, counts)
         return out.detach(), cam_max
 

@@ -265,3 +265,33 @@ def test_seeder_computes_component_roi_when_none_is_given(torch_cuda):
     torch.manual_seed(5)
     b = seeder(cam, roi)
     assert torch.equal(a, b)
+
+
+def test_seeder_without_host_round_trip(torch_cuda):
+    """rng_parity=False: candidate counts stay on the GPU (no host sync, fixed draw slots).  The counts must equal the
+    host-computed ones -- flat CAMs, empty rois and float32 truncation of max_p * roi.sum() included -- and every
+    foreground seed must be one of the n best roi pixels, every background seed one of the n lowest pixels."""
+    torch = torch_cuda
+    cam, roi = _make(torch, 6, 64, 80, seed=33)
+    cam[2] = 0.25                       # flat: no seeds at all (tcam_seeding.py:465)
+    roi[3] = 0                          # empty roi: no foreground candidates
+    seeder = _seeder(rng_parity=False, ksz=1, max_=3, min_=2)
+    x, r = seeder._prep(cam, roi)
+    host_counts, _ = seeder._candidate_counts(x, r)
+    dev_counts = seeder._candidate_counts_device(x, r)
+    assert dev_counts.dtype == torch.int32 and np.array_equal(dev_counts.cpu().numpy(), host_counts)
+    out = seeder(cam, roi)
+    assert set(torch.unique(out).tolist()) <= {-255, 0, 1}
+    assert (out[2] == -255).all()
+    assert (out[3] != 1).all()
+    flat = cam.reshape(6, -1)
+    for i in (0, 1, 4, 5):
+        n_fg, n_bg = int(host_counts[i, 0]), int(host_counts[i, 1])
+        fg_vals = (flat[i] * roi[i].reshape(-1) + 1e-8)
+        thr_fg = torch.sort(fg_vals, descending=True).values[n_fg - 1]
+        thr_bg = torch.sort(flat[i] + 1e-8).values[n_bg - 1]
+        seeds_fg = (out[i].reshape(-1) == 1).nonzero().flatten()
+        seeds_bg = (out[i].reshape(-1) == 0).nonzero().flatten()
+        assert 1 <= seeds_fg.numel() <= 3 and 1 <= seeds_bg.numel() <= 2
+        assert (fg_vals[seeds_fg] >= thr_fg).all()
+        assert ((flat[i] + 1e-8)[seeds_bg] <= thr_bg).all()
