@@ -1,0 +1,108 @@
+"""Generates tests/golden/py/*.npz by EXECUTING the reference's own Python for the pure-torch / pure-python pieces
+around the hot path (no GPU, no third-party packages needed).  Run in the build container only:
+
+    python tests/golden/make_golden_py.py
+
+The reference package cannot be imported here (dlib/__init__ chains need pydensecrf, kornia, skimage, munch ...), so
+the function bodies are cut out of the reference files with `ast` -- from where they lie under /root/reference,
+nothing is copied into this repository -- compiled and run as they are:
+
+  * _WSOLDataset.re_normalize_cam, _get_lef_knn, _get_right_knn   dlib/datasets/wsol_loader.py:448-459, 630-635
+  * the torch.maximum chain of __getitem__                         dlib/datasets/wsol_loader.py:591-600 (restated:
+                                                                   three lines inside a 150-line method)
+  * Trainer.prepare_std_cams_disq                                  dlib/learning/train_wsol.py:417-432
+  * DenseCRFLossFunction.forward / backward arithmetic             (already pinned by make_golden.py)
+
+Stored: inputs and the reference functions' outputs.  tests/test_oracle.py checks the oracle restatements against
+them (CPU), tests/test_gpu_seeding.py the kernels (GPU box, where /root/reference does not exist).
+"""
+import ast
+import os
+import sys
+import textwrap
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tcam_wsol_video_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "py")
+
+
+def cut(path, cls, name):
+    """Source of method `name` of class `cls` in the reference file `path`, dedented, decorators dropped."""
+    src = open(os.path.join(REF, path)).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == name:
+                    lines = src.splitlines()[item.lineno - 1:item.end_lineno]
+                    return textwrap.dedent("\n".join(lines))
+    raise KeyError((path, cls, name))
+
+
+def load(path, cls, name, env):
+    code = cut(path, cls, name)
+    scope = dict(env)
+    exec(compile(code, f"{path}:{cls}.{name}", "exec"), scope)
+    return scope[name]
+
+
+def main():
+    from typing import Tuple
+    os.makedirs(OUT, exist_ok=True)
+    env = {"torch": torch, "F": F, "Tuple": Tuple}
+    loader_cls = "WSOLImageLabelDataset"
+    re_norm = load("dlib/datasets/wsol_loader.py", loader_cls, "re_normalize_cam", env)
+    left = load("dlib/datasets/wsol_loader.py", loader_cls, "_get_lef_knn", env)
+    right = load("dlib/datasets/wsol_loader.py", loader_cls, "_get_right_knn", env)
+    prep = load("dlib/learning/train_wsol.py", "Trainer", "prepare_std_cams_disq", env)
+
+    # --- temporal aggregation: B samples x T frames of low-resolution CAMs, with the odd values the loader guards
+    low = torch.from_numpy(synth.make_low_res_cams(6, 5, 28, 28, seed=11))          # [B,T,1,h,w]
+    low[1, 2, 0, 3, 4] = float("nan")
+    low[2, 0, 0, 0, 0] = float("inf")
+    low[3, 1, 0, 5, 5] = float("-inf")
+    out = {"cams": low.numpy()}
+    for h_t in (0.0, 10.0, 50.0):
+        agg = []
+        for b in range(low.shape[0]):
+            std = None
+            for t in range(low.shape[1]):
+                c = low[b, t]
+                if h_t > 0:
+                    c = re_norm(c, h=h_t)                                       # wsol_loader.py:594-595
+                std = c if std is None else torch.maximum(std, c)               # wsol_loader.py:597-600
+            agg.append(std)
+        out[f"agg_h{int(h_t)}"] = torch.stack(agg).numpy()
+    out["renorm_single_h10"] = re_norm(low[0, 0], h=10.0).numpy()
+    np.savez_compressed(os.path.join(OUT, "py_temporal_agg.npz"), **out)
+
+    # --- prepare_std_cams_disq (self is unused by the method body)
+    std = torch.from_numpy(synth.make_low_res_cams(3, 1, 28, 28, seed=4))[:, 0]       # [B,1,h,w]
+    std[0, 0, 2, 3] = float("nan")
+    std[1, 0, 0, 0] = float("inf")
+    std[2, 0, 27, 27] = float("-inf")
+    res = {"std_cams": std.numpy()}
+    for size in ((224, 224), (96, 160), (28, 28)):
+        res[f"out_{size[0]}x{size[1]}"] = prep(None, std, size).numpy()
+    np.savez_compressed(os.path.join(OUT, "py_prepare_std_cams.npz"), **res)
+
+    # --- frame pickers
+    frames = [f"shot0_{i:03d}.jpg" for i in range(7)]
+    pick = {}
+    for k in (1, 2, 4):
+        for f in (0, 1, 3, 5, 6):
+            pick[f"left_k{k}_f{f}"] = np.array(left(frames, frames[f], k), dtype=object).astype(str)
+            pick[f"right_k{k}_f{f}"] = np.array(right(frames, frames[f], k), dtype=object).astype(str)
+    np.savez_compressed(os.path.join(OUT, "py_frame_pickers.npz"), frames=np.array(frames), **pick)
+    print("wrote py_temporal_agg.npz, py_prepare_std_cams.npz, py_frame_pickers.npz")
+
+
+if __name__ == "__main__":
+    main()

@@ -295,3 +295,31 @@ def test_seeder_without_host_round_trip(torch_cuda):
         assert 1 <= seeds_fg.numel() <= 3 and 1 <= seeds_bg.numel() <= 2
         assert (fg_vals[seeds_fg] >= thr_fg).all()
         assert ((flat[i] + 1e-8)[seeds_bg] <= thr_bg).all()
+
+
+def test_temporal_kernels_match_the_reference_python(torch_cuda):
+    """The temporal-aggregation and CAM-resize kernels against fixtures produced by EXECUTING the reference's own
+    re_normalize_cam / torch.maximum loop / prepare_std_cams_disq on the CPU (tests/golden/make_golden_py.py).
+    Plain max: bit-exact.  exp-based re-normalisation and the bilinear resize: 1e-6 (CUDA expf / FMA contraction
+    against torch's CPU kernels)."""
+    import os
+    torch = torch_cuda
+    from conftest import GOLDEN
+    from tcam_wsol_video_b200 import temporal
+    g = np.load(os.path.join(GOLDEN, "py", "py_temporal_agg.npz"))
+    cams = torch.from_numpy(g["cams"]).cuda()
+    for h_t in (0.0, 10.0, 50.0):
+        got = temporal.aggregate_temporal_cams(cams, knn_t=h_t).cpu().numpy()
+        want = g[f"agg_h{int(h_t)}"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        a, b = np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0)
+        if h_t == 0.0:
+            assert np.array_equal(a, b)
+        else:
+            assert np.abs(a - b).max() <= 1e-6
+    g = np.load(os.path.join(GOLDEN, "py", "py_prepare_std_cams.npz"))
+    std = torch.from_numpy(g["std_cams"]).cuda()
+    for key in [k for k in g.files if k.startswith("out_")]:
+        size = tuple(int(v) for v in key[4:].split("x"))
+        got = temporal.prepare_std_cams_disq(std, size).cpu().numpy()
+        assert np.abs(got - g[key]).max() <= 1e-6, key

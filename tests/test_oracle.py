@@ -115,3 +115,40 @@ def test_loss_wrapper_restates_reference_lines(oracle_mod):
     assert AS.shape == seg.shape and grad.shape == seg.shape
     assert abs(float(loss) + float((seg.astype(np.float64) * AS).sum() / n)) < 1e-3 * abs(float(loss))
     assert np.allclose(grad, -2.0 * 0.25 * AS / n, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# fixtures made by EXECUTING the reference's own Python (tests/golden/make_golden_py.py)
+# ---------------------------------------------------------------------------
+def _py_golden(name):
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "py", name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def test_restatements_match_the_reference_python():
+    """oracle/seeding.py's re_normalize_cam / temporal max / prepare_std_cams_disq and the package's frame pickers
+    against outputs of the reference's own functions (cut out of wsol_loader.py / train_wsol.py and executed)."""
+    import torch
+    from oracle import seeding as oseed
+    from tcam_wsol_video_b200 import temporal as tp
+    g = _py_golden("py_temporal_agg.npz")
+    cams = torch.from_numpy(g["cams"])
+    for h_t in (0.0, 10.0, 50.0):
+        got = oseed.temporal_max_renorm(cams, h_t).numpy()
+        want = g[f"agg_h{int(h_t)}"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(np.nan_to_num(got, nan=-7.0), np.nan_to_num(want, nan=-7.0)), h_t   # same torch, same bits
+    assert np.array_equal(oseed.re_normalize_cam(cams[0, 0], 10.0).numpy(), g["renorm_single_h10"])
+    g = _py_golden("py_prepare_std_cams.npz")
+    std = torch.from_numpy(g["std_cams"])
+    for key in [k for k in g if k.startswith("out_")]:
+        size = tuple(int(v) for v in key[4:].split("x"))
+        assert np.array_equal(oseed.prepare_std_cams_disq(std, size).numpy(), g[key]), key
+    g = _py_golden("py_frame_pickers.npz")
+    frames = [str(f) for f in g["frames"]]
+    for key in [k for k in g if k.startswith(("left_", "right_"))]:
+        side, k, f = key.split("_")
+        fn = tp.get_left_knn if side == "left" else tp.get_right_knn
+        assert fn(frames, frames[int(f[1:])], int(k[1:])) == [str(v) for v in g[key]], key
