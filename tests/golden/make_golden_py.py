@@ -11,7 +11,10 @@ nothing is copied into this repository -- compiled and run as they are:
   * the torch.maximum chain of __getitem__                         dlib/datasets/wsol_loader.py:591-600 (restated:
                                                                    three lines inside a 150-line method)
   * Trainer.prepare_std_cams_disq                                  dlib/learning/train_wsol.py:417-432
-  * DenseCRFLossFunction.forward / backward arithmetic             (already pinned by make_golden.py)
+  * _SFG / _SBG (fg / bg seed sampling modules, whole classes)      dlib/cams/tcam_seeding.py:490-592
+  * DenseCRFLossFunction (whole class, forward + backward)          dlib/crf/dense_crf_loss.py:30-74, with the
+                                                                   reference's own C++ (oracle/_ref) behind the
+                                                                   bilateralfilter_batch name instead of the SWIG module
 
 Stored: inputs and the reference functions' outputs.  tests/test_oracle.py checks the oracle restatements against
 them (CPU), tests/test_gpu_seeding.py the kernels (GPU box, where /root/reference does not exist).
@@ -44,6 +47,21 @@ def cut(path, cls, name):
                     lines = src.splitlines()[item.lineno - 1:item.end_lineno]
                     return textwrap.dedent("\n".join(lines))
     raise KeyError((path, cls, name))
+
+
+def cut_class(path, cls):
+    """Source of a whole top-level class of the reference file `path`."""
+    src = open(os.path.join(REF, path)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            return "\n".join(src.splitlines()[node.lineno - 1:node.end_lineno])
+    raise KeyError((path, cls))
+
+
+def load_class(path, cls, env):
+    scope = dict(env)
+    exec(compile(cut_class(path, cls), f"{path}:{cls}", "exec"), scope)
+    return scope[cls]
 
 
 def load(path, cls, name, env):
@@ -101,7 +119,60 @@ def main():
             pick[f"left_k{k}_f{f}"] = np.array(left(frames, frames[f], k), dtype=object).astype(str)
             pick[f"right_k{k}_f{f}"] = np.array(right(frames, frames[f], k), dtype=object).astype(str)
     np.savez_compressed(os.path.join(OUT, "py_frame_pickers.npz"), frames=np.array(frames), **pick)
-    print("wrote py_temporal_agg.npz, py_prepare_std_cams.npz, py_frame_pickers.npz")
+    # --- fg / bg seed sampling: the reference's own _SFG / _SBG modules (dlib/cams/tcam_seeding.py:490-592) on the
+    #     CPU generator; oracle/seeding.py must reproduce them draw for draw
+    import types
+    import torch.nn as nn
+    consts = types.SimpleNamespace(SEED_UNIFORM='seed_uniform', SEED_WEIGHTED='seed_weighted')
+    senv = {"torch": torch, "nn": nn, "constants": consts}
+    SFG = load_class("dlib/cams/tcam_seeding.py", "_SFG", senv)
+    SBG = load_class("dlib/cams/tcam_seeding.py", "_SBG", senv)
+    g = torch.Generator().manual_seed(77)
+    lowc = torch.rand((4, 1, 7, 9), generator=g)
+    cam = F.interpolate(lowc, size=(48, 56), mode="bilinear", align_corners=False)[:, 0]
+    cam[3] = torch.round(cam[3] * 8) / 8                                      # many ties: stable-sort order matters
+    roi = (cam >= cam.flatten(1).median(dim=1).values.view(4, 1, 1)).long()
+    seeds = {"cam": cam.numpy(), "roi": roi.numpy()}
+    for ci, (tech, max_, min_, max_p, min_p, use_roi) in enumerate([
+            ('seed_weighted', 1, 1, 0.6, 0.1, True), ('seed_uniform', 1, 1, 0.6, 0.1, True),
+            ('seed_weighted', 5, 3, 0.2, 0.2, False), ('seed_uniform', 10, 10, 0.2, 0.2, True)]):
+        fgm, bgm = SFG(max_p=max_p, max_=max_, seed_tech=tech), SBG(min_p=min_p, min_=min_, seed_tech='seed_uniform')
+        torch.manual_seed(1000 + ci)
+        fgs, bgs = [], []
+        for i in range(cam.shape[0]):                                          # TCAMSeeder's per-sample order
+            fg0 = torch.zeros((48, 56), dtype=torch.long)
+            bg0 = torch.zeros((48, 56), dtype=torch.long)
+            fgs.append(fgm(cam=cam[i], roi=roi[i] if use_roi else None, fg=fg0))
+            bgs.append(bgm(cam=cam[i], bg=bg0))
+        seeds[f"case{ci}_fg"] = torch.stack(fgs).numpy()
+        seeds[f"case{ci}_bg"] = torch.stack(bgs).numpy()
+        seeds[f"case{ci}_cfg"] = np.array([tech, str(max_), str(min_), str(max_p), str(min_p), str(int(use_roi))])
+    np.savez_compressed(os.path.join(OUT, "py_seed_sampling.npz"), **seeds)
+    # --- DenseCRFLossFunction itself (dlib/crf/dense_crf_loss.py:30-74), run on CPU tensors: the SWIG module is
+    #     replaced by the reference's own C++ built in place (oracle/_ref), torch.cuda.synchronize() by a no-op (there
+    #     is no GPU in the build container), the AMP decorators by the identity
+    import oracle
+    if oracle.have_ref():
+        def bilateralfilter_batch(images, ins, outs, N, K, H, W, sigma_rgb, sigma_xy):
+            outs[:] = oracle.ref_bilateralfilter_batch(images, ins, N, K, H, W, sigma_rgb, sigma_xy)
+        ident = lambda f: f
+        fenv = {"torch": torch, "np": np, "Function": torch.autograd.Function, "custom_fwd": ident,
+                "custom_bwd": ident, "bilateralfilter_batch": bilateralfilter_batch}
+        real_sync = torch.cuda.synchronize
+        torch.cuda.synchronize = lambda *a, **k: None
+        try:
+            Fn = load_class("dlib/crf/dense_crf_loss.py", "DenseCRFLossFunction", fenv)
+            n, k, h, w = 2, 3, 31, 37
+            img = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=5))
+            seg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=5)).requires_grad_(True)
+            loss = 1e-3 * Fn.apply(img, seg, 15.0, 100.0)
+            loss.backward()
+        finally:
+            torch.cuda.synchronize = real_sync
+        np.savez_compressed(os.path.join(OUT, "py_dense_crf_loss.npz"), image=img.numpy(), seg=seg.detach().numpy(),
+                            loss=loss.detach().numpy(), grad=seg.grad.numpy(), weight=np.float32(1e-3))
+    print("wrote py_temporal_agg.npz, py_prepare_std_cams.npz, py_frame_pickers.npz, py_seed_sampling.npz, "
+          "py_dense_crf_loss.npz")
 
 
 if __name__ == "__main__":

@@ -234,3 +234,19 @@ def test_dense_crf_filter_mean_field(torch_cuda, oracle_mod, shape, quirk):
     assert np.abs(got.numpy() - seg.numpy()).max() > 1e-2
     same = DenseCRFFilter(15, 100, 1.0, 0)(torch.from_numpy(raw_np), seg)
     assert torch.equal(same, seg)
+
+
+def test_module_matches_the_reference_autograd_function(torch_cuda):
+    """DenseCRFLoss (CUDA) against loss and gradient produced by the reference's own DenseCRFLossFunction executed on
+    CPU tensors with the reference's C++ behind it (tests/golden/py/py_dense_crf_loss.npz)."""
+    import os
+    torch = torch_cuda
+    from conftest import GOLDEN
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    g = np.load(os.path.join(GOLDEN, "py", "py_dense_crf_loss.npz"))
+    seg = torch.from_numpy(g["seg"]).cuda().requires_grad_(True)
+    loss = DenseCRFLoss(float(g["weight"]), 15.0, 100.0, 1.0)(images=torch.from_numpy(g["image"]), segmentations=seg)
+    loss.backward()
+    assert loss.shape == (1,)
+    assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
+    assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL

@@ -152,3 +152,37 @@ def test_restatements_match_the_reference_python():
         side, k, f = key.split("_")
         fn = tp.get_left_knn if side == "left" else tp.get_right_knn
         assert fn(frames, frames[int(f[1:])], int(k[1:])) == [str(v) for v in g[key]], key
+
+
+def test_seed_sampling_restatement_matches_the_reference_modules():
+    """oracle/seeding.py's sample_fg / sample_bg against the reference's own _SFG / _SBG modules executed on the CPU
+    generator with the same seed (tests/golden/make_golden_py.py): same stable sort, same candidate order, same
+    multinomial draws -> identical seed maps."""
+    import torch
+    from oracle import seeding as oseed
+    g = _py_golden("py_seed_sampling.npz")
+    cam, roi = torch.from_numpy(g["cam"]), torch.from_numpy(g["roi"])
+    ci = 0
+    while f"case{ci}_cfg" in g:
+        tech, max_, min_, max_p, min_p, use_roi = [str(v) for v in g[f"case{ci}_cfg"]]
+        torch.manual_seed(1000 + ci)
+        for i in range(cam.shape[0]):
+            fg = oseed.sample_fg(cam[i], roi[i] if use_roi == "1" else None, torch.zeros((48, 56), dtype=torch.long),
+                                 float(max_p), int(max_), tech)
+            bg = oseed.sample_bg(cam[i], torch.zeros((48, 56), dtype=torch.long), float(min_p), int(min_))
+            assert np.array_equal(fg.numpy(), g[f"case{ci}_fg"][i]), (ci, i)
+            assert np.array_equal(bg.numpy(), g[f"case{ci}_bg"][i]), (ci, i)
+        ci += 1
+    assert ci == 4
+
+
+def test_loss_restatement_matches_the_reference_autograd_function(oracle_mod):
+    """oracle.densecrf_loss_fwd_bwd (the 15 restated lines) against the reference's own DenseCRFLossFunction executed
+    on CPU tensors with the reference's C++ behind it (tests/golden/make_golden_py.py).  The filter is bit-identical;
+    the loss sums 2*3*31*37 float32 products in torch's order there and numpy's here: rel 1e-6."""
+    g = _py_golden("py_dense_crf_loss.npz")
+    w = float(g["weight"])
+    loss, grad, _ = oracle_mod.densecrf_loss_fwd_bwd(g["image"], g["seg"], 15.0, 100.0, w,
+                                                    oracle_mod.port_bilateralfilter_batch)
+    assert abs(w * float(loss) - float(g["loss"][0])) <= 1e-6 * abs(float(g["loss"][0]))
+    assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()
