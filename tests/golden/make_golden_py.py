@@ -171,8 +171,31 @@ def main():
             torch.cuda.synchronize = real_sync
         np.savez_compressed(os.path.join(OUT, "py_dense_crf_loss.npz"), image=img.numpy(), seg=seg.detach().numpy(),
                             loss=loss.detach().numpy(), grad=seg.grad.numpy(), weight=np.float32(1e-3))
+    # --- clip grouping of the joint colour CRF (dlib/losses/tcam.py:32-45 group_ordered_frames, :207-232 pair_samples)
+    src = open(os.path.join(REF, "dlib/losses/tcam.py")).read()
+    gscope = {"torch": torch, "Tuple": Tuple}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "group_ordered_frames":
+            exec(compile("\n".join(src.splitlines()[node.lineno - 1:node.end_lineno]), "tcam.py", "exec"), gscope)
+    pair = load("dlib/losses/tcam.py", "RgbJointConRanFieldTcams", "pair_samples", gscope)
+    seq_iter = torch.tensor([3., 1., 3., 1., 7., 3., 1., 3.])
+    frm_iter = torch.tensor([2., 0., 0., 1., 0., 1., 2., 3.])
+    groups = gscope["group_ordered_frames"](seq_iter, frm_iter)
+    groups = [[int(i) for i in grp] for grp in groups]
+    gen = torch.Generator().manual_seed(3)
+    imgs = torch.randint(0, 256, (8, 3, 6, 5), generator=gen).float()
+    probs = torch.rand((8, 2, 6, 5), generator=gen)
+    clip = {"seq_iter": seq_iter.numpy(), "frm_iter": frm_iter.numpy(), "imgs": imgs.numpy(), "probs": probs.numpy(),
+            "n_groups": np.int64(len(groups))}
+    for gi, grp in enumerate(groups):
+        clip[f"group{gi}"] = np.array(grp, dtype=np.int64)
+        if len(grp) > 1:
+            pi, pc = pair(o_idx=grp, imgs=imgs, prob_cams=probs)
+            clip[f"pair{gi}_img"] = pi.numpy()
+            clip[f"pair{gi}_cam"] = pc.numpy()
+    np.savez_compressed(os.path.join(OUT, "py_clip_grouping.npz"), **clip)
     print("wrote py_temporal_agg.npz, py_prepare_std_cams.npz, py_frame_pickers.npz, py_seed_sampling.npz, "
-          "py_dense_crf_loss.npz")
+          "py_dense_crf_loss.npz, py_clip_grouping.npz")
 
 
 if __name__ == "__main__":

@@ -186,3 +186,19 @@ def test_loss_restatement_matches_the_reference_autograd_function(oracle_mod):
                                                     oracle_mod.port_bilateralfilter_batch)
     assert abs(w * float(loss) - float(g["loss"][0])) <= 1e-6 * abs(float(g["loss"][0]))
     assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()
+
+
+def test_clip_grouping_matches_the_reference_functions():
+    """losses.group_ordered_frames / RgbJointConRanFieldTcams.pair_samples against the reference's own functions
+    (dlib/losses/tcam.py:32-45, 207-232) executed by tests/golden/make_golden_py.py."""
+    import torch
+    from tcam_wsol_video_b200.losses import RgbJointConRanFieldTcams, group_ordered_frames
+    g = _py_golden("py_clip_grouping.npz")
+    groups = group_ordered_frames(torch.from_numpy(g["seq_iter"]), torch.from_numpy(g["frm_iter"]))
+    assert len(groups) == int(g["n_groups"])
+    imgs, probs = torch.from_numpy(g["imgs"]), torch.from_numpy(g["probs"])
+    for gi, grp in enumerate(groups):
+        assert list(grp) == g[f"group{gi}"].tolist()
+        if len(grp) > 1:
+            pi, pc = RgbJointConRanFieldTcams.pair_samples(o_idx=grp, imgs=imgs, prob_cams=probs)
+            assert np.array_equal(pi.numpy(), g[f"pair{gi}_img"]) and np.array_equal(pc.numpy(), g[f"pair{gi}_cam"])
