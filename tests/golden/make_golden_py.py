@@ -171,6 +171,23 @@ def main():
             torch.cuda.synchronize = real_sync
         np.savez_compressed(os.path.join(OUT, "py_dense_crf_loss.npz"), image=img.numpy(), seg=seg.detach().numpy(),
                             loss=loss.detach().numpy(), grad=seg.grad.numpy(), weight=np.float32(1e-3))
+        # ... and ColorDenseCRFLossFunction (dlib/crf/color_dense_crf_loss.py:33-76) on a width-concatenated clip
+        def colorbilateralfilter_batch(images, ins, outs, N, K, H, W, sigma_rgb, DIM):
+            outs[:] = oracle.ref_colorbilateralfilter_batch(images, ins, N, K, H, W, sigma_rgb, DIM)
+        cenv = dict(fenv, colorbilateralfilter_batch=colorbilateralfilter_batch)
+        torch.cuda.synchronize = lambda *a, **k: None
+        try:
+            CFn = load_class("dlib/crf/color_dense_crf_loss.py", "ColorDenseCRFLossFunction", cenv)
+            n, k, h, w = 2, 2, 24, 3 * 20
+            cimg = torch.from_numpy(synth.make_images(n, h, w, "natural", seed=6))
+            cseg = torch.from_numpy(synth.make_segs(n, k, h, w, seed=6)).requires_grad_(True)
+            closs = 1e-3 * CFn.apply(cimg, cseg, 15.0)
+            closs.backward()
+        finally:
+            torch.cuda.synchronize = real_sync
+        np.savez_compressed(os.path.join(OUT, "py_color_dense_crf_loss.npz"), image=cimg.numpy(),
+                            seg=cseg.detach().numpy(), loss=closs.detach().numpy(), grad=cseg.grad.numpy(),
+                            weight=np.float32(1e-3))
     # --- clip grouping of the joint colour CRF (dlib/losses/tcam.py:32-45 group_ordered_frames, :207-232 pair_samples)
     src = open(os.path.join(REF, "dlib/losses/tcam.py")).read()
     gscope = {"torch": torch, "Tuple": Tuple}

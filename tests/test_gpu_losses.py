@@ -250,3 +250,17 @@ def test_module_matches_the_reference_autograd_function(torch_cuda):
     assert loss.shape == (1,)
     assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
     assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL
+
+
+def test_colour_module_matches_the_reference_autograd_function(torch_cuda):
+    """ColorDenseCRFLoss (CUDA) against the reference's own ColorDenseCRFLossFunction executed on CPU tensors."""
+    import os
+    torch = torch_cuda
+    from conftest import GOLDEN
+    from tcam_wsol_video_b200.color_dense_crf_loss import ColorDenseCRFLoss
+    g = np.load(os.path.join(GOLDEN, "py", "py_color_dense_crf_loss.npz"))
+    seg = torch.from_numpy(g["seg"]).cuda().requires_grad_(True)
+    loss = ColorDenseCRFLoss(float(g["weight"]), 15.0, 1.0)(images=torch.from_numpy(g["image"]), segmentations=seg)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
+    assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL

@@ -202,3 +202,12 @@ def test_clip_grouping_matches_the_reference_functions():
         if len(grp) > 1:
             pi, pc = RgbJointConRanFieldTcams.pair_samples(o_idx=grp, imgs=imgs, prob_cams=probs)
             assert np.array_equal(pi.numpy(), g[f"pair{gi}_img"]) and np.array_equal(pc.numpy(), g[f"pair{gi}_cam"])
+
+
+def test_colour_loss_restatement_matches_the_reference_autograd_function(oracle_mod):
+    g = _py_golden("py_color_dense_crf_loss.npz")
+    w = float(g["weight"])
+    loss, grad, _ = oracle_mod.color_densecrf_loss_fwd_bwd(g["image"], g["seg"], 15.0, w,
+                                                          oracle_mod.port_colorbilateralfilter_batch)
+    assert abs(w * float(loss) - float(g["loss"][0])) <= 1e-6 * abs(float(g["loss"][0]))
+    assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()
