@@ -12,6 +12,8 @@ nothing is copied into this repository -- compiled and run as they are:
                                                                    three lines inside a 150-line method)
   * Trainer.prepare_std_cams_disq                                  dlib/learning/train_wsol.py:417-432
   * _SFG / _SBG (fg / bg seed sampling modules, whole classes)      dlib/cams/tcam_seeding.py:490-592
+  * TCAMSeeder + _OneSample (whole classes; kornia's dilation and  dlib/cams/tcam_seeding.py:44-260, 433-488
+    torch.device(cuda_id) stubbed, see below)
   * DenseCRFLossFunction (whole class, forward + backward)          dlib/crf/dense_crf_loss.py:30-74, with the
                                                                    reference's own C++ (oracle/_ref) behind the
                                                                    bilateralfilter_batch name instead of the SWIG module
@@ -148,6 +150,47 @@ def main():
         seeds[f"case{ci}_bg"] = torch.stack(bgs).numpy()
         seeds[f"case{ci}_cfg"] = np.array([tech, str(max_), str(min_), str(max_p), str(min_p), str(int(use_roi))])
     np.savez_compressed(os.path.join(OUT, "py_seed_sampling.npz"), **seeds)
+    # --- the whole TCAMSeeder.forward (dlib/cams/tcam_seeding.py:44-260 + _OneSample :433-488) on the CPU: per-sample
+    #     loop, dilation of the seed maps, fg/bg conflict cancellation, ignore index.  Two things are stubbed and said
+    #     so: kornia's dilation / erosion (not installed) by the flat max-pool of oracle/seeding.py, and
+    #     torch.device(cuda_id) by the CPU device (no GPU in the build container).  roi is always passed, so the
+    #     skimage-based GetRoiSingleCam / STOtsu members are constructed as dummies and never called.
+    from oracle import seeding as oseed
+
+    class _TorchOnCpu:
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def device(*_a, **_k):
+            return torch.device("cpu")
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+
+    from typing import Callable
+    consts2 = types.SimpleNamespace(SEED_UNIFORM='seed_uniform', SEED_WEIGHTED='seed_weighted',
+                                    SEED_TECHS=['seed_uniform', 'seed_weighted'],
+                                    ROI_SELECT=['roi_all', 'roi_high_density', 'largest'])
+    tenv = {"torch": _TorchOnCpu(), "nn": nn, "constants": consts2, "Tuple": Tuple, "Callable": Callable,
+            "STOtsu": _Dummy, "GetRoiSingleCam": _Dummy,
+            "dilation": lambda x, kernel: oseed.flat_dilation(x, kernel.shape[0]),
+            "erosion": lambda x, kernel: -oseed.flat_dilation(-x, kernel.shape[0])}
+    for cname in ("_SFG", "_SBG", "_OneSample", "TCAMSeeder"):
+        exec(compile(cut_class("dlib/cams/tcam_seeding.py", cname), f"tcam_seeding.py:{cname}", "exec"), tenv)
+    full = {"cam": cam.numpy(), "roi": roi.numpy()}
+    for ci, kw in enumerate([
+            dict(seed_tech='seed_weighted', min_=1, max_=1, min_p=0.1, max_p=0.6, ksz=3, use_roi=True),
+            dict(seed_tech='seed_uniform', min_=10, max_=10, min_p=0.2, max_p=0.2, ksz=1, use_roi=False),
+            dict(seed_tech='seed_weighted', min_=4, max_=4, min_p=0.3, max_p=0.3, ksz=5, use_roi=True)]):
+        mod = tenv["TCAMSeeder"](fg_erode_k=11, fg_erode_iter=0, support_background=True, multi_label_flag=False,
+                                 seg_ignore_idx=-255, cuda_id=0, roi_method='roi_all', p_min_area_roi=0.05, **kw)
+        torch.manual_seed(2000 + ci)
+        full[f"case{ci}_out"] = mod(cam.unsqueeze(1), roi.unsqueeze(1)).numpy()
+        full[f"case{ci}_cfg"] = np.array([f"{k}={v}" for k, v in kw.items()])
+    np.savez_compressed(os.path.join(OUT, "py_tcam_seeder.npz"), **full)
+
     # --- DenseCRFLossFunction itself (dlib/crf/dense_crf_loss.py:30-74), run on CPU tensors: the SWIG module is
     #     replaced by the reference's own C++ built in place (oracle/_ref), torch.cuda.synchronize() by a no-op (there
     #     is no GPU in the build container), the AMP decorators by the identity

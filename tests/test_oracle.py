@@ -211,3 +211,24 @@ def test_colour_loss_restatement_matches_the_reference_autograd_function(oracle_
                                                           oracle_mod.port_colorbilateralfilter_batch)
     assert abs(w * float(loss) - float(g["loss"][0])) <= 1e-6 * abs(float(g["loss"][0]))
     assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()
+
+
+def test_seeder_forward_restatement_matches_the_reference_module():
+    """oracle/seeding.py's tcam_seeder_forward against the reference's own TCAMSeeder.forward executed on the CPU
+    generator (kornia's dilation replaced by the flat max-pool, torch.device(cuda_id) by the CPU device)."""
+    import torch
+    from oracle import seeding as oseed
+    g = _py_golden("py_tcam_seeder.npz")
+    cam, roi = torch.from_numpy(g["cam"]).unsqueeze(1), torch.from_numpy(g["roi"]).unsqueeze(1)
+    ci = 0
+    while f"case{ci}_cfg" in g:
+        kw = {}
+        for item in g[f"case{ci}_cfg"]:
+            key, val = str(item).split("=")
+            kw[key] = val if key == "seed_tech" else (val == "True" if key == "use_roi" else
+                                                       (float(val) if key in ("min_p", "max_p") else int(val)))
+        torch.manual_seed(2000 + ci)
+        got = oseed.tcam_seeder_forward(cam, roi, ignore_idx=-255, **kw)
+        assert np.array_equal(got.numpy(), g[f"case{ci}_out"]), ci
+        ci += 1
+    assert ci == 3
