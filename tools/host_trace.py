@@ -1,5 +1,6 @@
+"""Timeline of one tcamcrf_loss_fwd_bwd_host call (TCAMCRF_HOST_TRACE=1): python tools/host_trace.py [K]"""
 import ctypes, sys, os, time, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tcam_wsol_video_b200 import _lib, synth
 lib=_lib.load()
 N,K,H,W=32,int(sys.argv[1]) if len(sys.argv)>1 else 10,224,224
