@@ -766,6 +766,7 @@ struct PixelParams {
     float n_norm;
     int P, K, Kp;
     int frame0;             // workspace frame of blockIdx.y == 0 (segs / as_out already point at that frame)
+    int dense;              // host-side hint: the lattices of this workspace have been dense lately (splat variant)
     long long pool;
     float alpha;
 };
@@ -868,6 +869,137 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
             }
             if (issue) red_add(p.values + (size_t)id[r] * p.Kp + k, t);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-cooperative splat for value rows of 2..4 float4s (K = 5..16), used on DENSE lattices.
+//
+// splat_kernel touches a vertex row with KV separate 16-byte REDs per thread: 32 lanes x KV instructions =
+// 32*KV requests to L2 per remainder, and on iid-noise frames (every pixel on its own vertices) the request rate of
+// the L2 (~180 G/s, profiles/README.md) is what bounds the kernel.  Here KV neighbouring lanes share one pixel and
+// each handles one float4 column of the row, so the KV REDs of a row sit in one instruction and leave the SM as ONE
+// request (two when the row straddles a 128-byte line): a third of the requests at K = 10 (0.205 -> 0.177 ms per 32
+// noise frames).  Per-pixel inputs are fetched with coalesced accesses and handed to the (pixel, column) lanes
+// through shared memory.  On real frames the pixel kernel wins (runs of equal vertices merge over the 32 pixels of
+// a warp instead of 32 / KV, no block barrier: 0.135 against 0.152 ms), so the host picks per call from the vertex
+// density of the previous calls on the workspace (density_hint below): a hint, never a correctness matter.
+template <int KV>
+__host__ __device__ constexpr unsigned int stride_bits(int count)   // bits KV, 2*KV, ..., count*KV
+{
+    unsigned int m = 0;
+    for (int i = 1; i <= count; i++) m |= 1u << (i * KV);
+    return m;
+}
+
+template <int KV>
+struct RowMap {
+    static constexpr int kPpw = 32 / KV;                       // pixels per warp
+    static constexpr int kPpb = (kThreads / 32) * kPpw;        // pixels per block
+};
+
+template <int D, int KV, bool L>
+__global__ void __launch_bounds__(kThreads) splat_rows_kernel(const PixelParams p)
+{
+    constexpr int kPpw = RowMap<KV>::kPpw, kPpb = RowMap<KV>::kPpb;
+    constexpr int Kp = 4 * KV;
+    __shared__ int s_raw[D + 1][kPpb];     // offset[] as stored (entry index, tagged id or -1)
+    __shared__ int s_id[D + 1][kPpb];
+    __shared__ float s_w[D + 1][kPpb];
+    __shared__ float s_seg[4 * KV][kPpb];
+    const int n = blockIdx.y;
+    const int pix0 = blockIdx.x * kPpb;
+    const int npix = min(kPpb, p.P - pix0);
+    const size_t base = (size_t)(p.frame0 + n) * (D + 1) * p.P + pix0;
+    // ahead of the wait (see splat_kernel): coalesced loads, id look-ups
+    for (int t = threadIdx.x; t < (D + 1) * kPpb; t += kThreads) {
+        const int r = t / kPpb, q = t - r * kPpb;
+        int raw = -1, v = -1;
+        float w = 0.f;
+        if (q < npix) {
+            raw = p.offset[base + (size_t)r * p.P + q];
+            if (raw >= 0)
+                v = __ldg(&p.table[raw].id);
+            else if (raw <= -2)
+                v = -2 - raw;
+            w = p.bary[base + (size_t)r * p.P + q];
+        }
+        s_raw[r][q] = raw;
+        s_id[r][q] = v;
+        s_w[r][q] = w;
+    }
+    const float *seg = p.segs + (size_t)n * p.K * p.P + pix0;
+    for (int t = threadIdx.x; t < Kp * kPpb; t += kThreads) {
+        const int k = t / kPpb, q = t - k * kPpb;
+        s_seg[k][q] = (k < p.K && q < npix) ? __ldg(seg + (size_t)k * p.P + q) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane / KV, c = lane - j * KV;                // pixel slot within the warp, float4 column
+    const bool lane_on = j < kPpw;
+    const int q = warp * kPpw + (lane_on ? j : 0);             // pixel slot within the block
+    const bool valid = lane_on && q < npix;
+    int id[D + 1];
+    float w[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        id[r] = valid ? s_id[r][q] : -1;
+        w[r] = valid ? s_w[r][q] : 0.f;
+    }
+    float s[4];
+    if (L) {   // softmax over the K planes of this pixel, torch's order of operations (see softmax_stat)
+        float zmax = -INFINITY, sum = 0.f;
+        for (int k = 0; k < p.K; k++) zmax = fmaxf(zmax, s_seg[k][q]);
+        for (int k = 0; k < p.K; k++) sum += expf(s_seg[k][q] - zmax);
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            s[e] = (valid && 4 * c + e < p.K) ? __fdiv_rn(expf(s_seg[4 * c + e][q] - zmax), sum) : 0.f;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) s[e] = valid ? s_seg[4 * c + e][q] : 0.f;
+    }
+    pdl_wait();   // the value rows are cleared by the previous kernel
+    pdl_launch_dependents();
+    // entry indices become tagged vertex ids (coalesced write-back of the fresh ones)
+    for (int t = threadIdx.x; t < (D + 1) * kPpb; t += kThreads) {
+        const int r = t / kPpb, qq = t - r * kPpb;
+        if (s_raw[r][qq] >= 0) {
+            const int v = s_id[r][qq];
+            p.offset[base + (size_t)r * p.P + qq] = v < 0 ? -1 : -2 - v;
+        }
+    }
+    unsigned int heads[D + 1];
+    bool any_run = false;
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        // runs of neighbouring PIXELS on the same vertex (lanes KV apart); idle lanes end every run
+        const int v = id[r];
+        const int left = __shfl_up_sync(0xffffffffu, v, KV);
+        const bool head = j == 0 || left != v || !lane_on;
+        heads[r] = __ballot_sync(0xffffffffu, head);
+        any_run |= heads[r] != 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) t[e] = __fmul_rn(w[r], s[e]);
+        bool issue = id[r] >= 0;
+        if (any_run && heads[r] != 0xffffffffu) {   // warp-uniform
+            // segmented suffix sum over the run: pixel j adds pixel j+o when no head lies in (j, j+o]
+            const unsigned int above = heads[r] >> lane;   // bit i*KV = head flag of pixel j+i (same column)
+#pragma unroll
+            for (int o = 1; o < kPpw; o <<= 1) {
+                const bool take = (j + o < kPpw) && ((above & stride_bits<KV>(o)) == 0u);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float other = __shfl_down_sync(0xffffffffu, t[e], o * KV);
+                    if (take) t[e] += other;
+                }
+            }
+            issue = issue && ((heads[r] >> lane) & 1u);
+        }
+        if (issue) red_add(p.values + (size_t)id[r] * Kp + 4 * c, t);
     }
 }
 
@@ -1204,9 +1336,27 @@ static void launch_pixel_v(bool splat, const PixelParams &pp, dim3 grid, cudaStr
     }
 }
 
+template <int D, int KV>
+static void launch_splat_rows(const PixelParams &pp, int frames, cudaStream_t st)
+{
+    const dim3 grid((pp.P + RowMap<KV>::kPpb - 1) / RowMap<KV>::kPpb, frames);
+    if (pp.logits)
+        launch_chained(splat_rows_kernel<D, KV, true>, grid, st, pp);
+    else
+        launch_chained(splat_rows_kernel<D, KV, false>, grid, st, pp);
+}
+
 template <int D>
 static void launch_pixel(bool splat, int V, const PixelParams &pp, dim3 grid, cudaStream_t st)
 {
+    if (splat && pp.dense && V == 4) {
+        switch (pp.Kp / 4) {   // rows of 2..4 float4s (K = 5..16)
+        case 2: return launch_splat_rows<D, 2>(pp, grid.y, st);
+        case 3: return launch_splat_rows<D, 3>(pp, grid.y, st);
+        case 4: return launch_splat_rows<D, 4>(pp, grid.y, st);
+        default: break;
+        }
+    }
     if (V == 4)
         launch_pixel_v<D, 4>(splat, pp, grid, st);
     else if (V == 2)
@@ -1305,6 +1455,90 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
     return TCAMCRF_OK;
 }
 
+// (the density hint is refreshed by the callers AFTER the value stages: an asynchronous copy between the
+// neighbour kernel and the splat would break the programmatic launch chain)
+
+// Vertex density of the recent calls on a workspace, for the HOST: after every lattice build the largest per-frame
+// vertex count (kCtrlPrevMax) is copied into a pinned word with an asynchronous device-to-host copy on the caller's
+// stream -- no synchronisation; the next calls read whatever has arrived (one or two calls old).  It only selects
+// between kernels that are both correct for every input.
+#ifndef TCAMCRF_DENSITY_HINT
+#define TCAMCRF_DENSITY_HINT 1
+#endif
+struct DensityHints {
+    std::mutex mu;
+    std::vector<std::pair<void *, int *>> slots;   // workspace -> pinned word (a handful of workspaces per process)
+    cudaStream_t side = nullptr;                   // the copies run here, off the caller's stream
+    cudaEvent_t ev = nullptr;
+    int device = -1;
+    int *find(void *ws, bool create)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto &s : slots)
+            if (s.first == ws) return s.second;
+        if (!create) return nullptr;
+        int *p = nullptr;
+        if (cudaHostAlloc((void **)&p, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *p = 0;
+        slots.emplace_back(ws, p);
+        return p;
+    }
+};
+static DensityHints g_hints;
+
+static bool stream_is_capturing(cudaStream_t st)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &status) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return status != cudaStreamCaptureStatusNone;
+}
+
+// largest per-frame vertex count seen lately on this workspace (0: unknown)
+static int density_hint(void *ws)
+{
+    if (!TCAMCRF_DENSITY_HINT) return 0;
+    int *slot = g_hints.find(ws, false);
+    return slot ? *(volatile int *)slot : 0;
+}
+
+// Queue the refresh of the hint behind the work already on `st`, on a side stream: the caller's stream never waits
+// for the copy (in-stream it costs ~5 us per call, more than the hint is worth on short steps).  Nothing is done
+// while a graph is being captured (an unjoined fork is not capturable; the hint then keeps its last value).
+static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
+{
+    if (!TCAMCRF_DENSITY_HINT) return;
+    // every 8th call is plenty for a hint (the three driver calls below cost ~10 us of host time, which shows on
+    // 0.25 ms steps); the first two calls on a workspace always refresh
+    static thread_local unsigned int calls = 0;
+    const unsigned int c = calls++;
+    if (c >= 2 && (c & 7u) != 0) return;
+    if (stream_is_capturing(st)) return;
+    int *slot = g_hints.find(ws, true);
+    if (!slot) return;
+    std::lock_guard<std::mutex> lock(g_hints.mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (g_hints.device != dev || !g_hints.side) {   // one process drives one GPU; re-create if that ever changes
+        if (cudaStreamCreateWithFlags(&g_hints.side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_hints.ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            g_hints.side = nullptr;
+            return;
+        }
+        g_hints.device = dev;
+    }
+    cudaEventRecord(g_hints.ev, st);
+    cudaStreamWaitEvent(g_hints.side, g_hints.ev, 0);
+    cudaMemcpyAsync(slot, ws + pl.off_ctrl + kCtrlPrevMax * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost,
+                    g_hints.side);
+}
+
 // Stage 2: splat -> blur x(d+1) -> slice (+ loss) for the frames [frame0, frame0 + nc) of a chunk whose lattice
 // is built.  segs / as_out point at frame0.  `zero_values`: the value rows were not cleared by lattice_stages.
 template <int D>
@@ -1348,6 +1582,8 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
     pp.K = pl.K;
     pp.Kp = pl.Kp;
     pp.frame0 = frame0;
+    // dense lattice lately (more than one vertex per four pixels in the fullest frame): row-cooperative splat
+    pp.dense = (long long)density_hint(ws) * 4 > (long long)pl.P ? 1 : 0;
     pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
     {
@@ -1416,7 +1652,9 @@ static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const v
 {
     int rc = run_lattice(cfg, pl, u8, images, 0, nc, ws, true, st);
     if (rc) return rc;
-    return run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
+    rc = run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
+    density_hint_refresh(pl, ws, st);
+    return rc;
 }
 
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
