@@ -1657,9 +1657,91 @@ static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const v
     return rc;
 }
 
+// Frames that are still in HOST memory (the reference's trainer keeps raw_img on the CPU, train_wsol.py:1128, and
+// hands it to DenseCRFLoss.forward every step): they are copied section by section on a copy stream of the
+// library while the lattice of the sections that have arrived is being built on the caller's stream, instead of
+// one copy followed by one build.  Fork/join with events only: nothing synchronises, and the pattern can be
+// captured in a CUDA graph (pinned source).
+struct CopyLane {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t next = 0;
+    int ready()
+    {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (device == dev && stream) return TCAMCRF_OK;
+        // one process drives one GPU; re-created if that ever changes (the old objects are leaked on purpose:
+        // work may still be queued on them)
+        CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        events.clear();
+        next = 0;
+        device = dev;
+        return TCAMCRF_OK;
+    }
+    int event(cudaEvent_t *ev)
+    {
+        if (events.size() < 64) {
+            cudaEvent_t e = nullptr;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            events.push_back(e);
+            *ev = e;
+            return TCAMCRF_OK;
+        }
+        *ev = events[next++ % events.size()];   // a waiter keeps the record it was given: re-recording is safe
+        return TCAMCRF_OK;
+    }
+};
+static CopyLane g_lane;
+
+// One chunk whose frames come from the host: `img_host` / `img_dev` point at frame 0 of the chunk.
+static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, const float *img_host, float *img_dev,
+                                 const float *segs, float *as_out, int nc, bool last_chunk, char *ws, bool want_loss,
+                                 float *loss_final, float n_norm, int flags, cudaStream_t st)
+{
+    // sections of at least 4 frames, 4 per chunk by default (32 frames: 8 + 8 + 8 + 8)
+    int nsec = 4;
+    if (const char *env = getenv("TCAMCRF_HIMG_SECTIONS")) {
+        const int v = atoi(env);
+        if (v >= 1 && v <= 64) nsec = v;
+    }
+    int per = (nc + nsec - 1) / nsec;
+    if (per < 4) per = nc < 4 ? nc : 4;
+    const size_t frame = (size_t)cfg->image_stride_planes * pl.P;   // floats per image
+    std::lock_guard<std::mutex> lock(g_lane.mu);
+    int rc = g_lane.ready();
+    if (rc) return rc;
+    cudaEvent_t ev;
+    rc = g_lane.event(&ev);
+    if (rc) return rc;
+    // the staging buffer may still be read by work queued earlier on the caller's stream
+    CUDA_TRY(cudaEventRecord(ev, st));
+    CUDA_TRY(cudaStreamWaitEvent(g_lane.stream, ev, 0));
+    for (int f0 = 0; f0 < nc; f0 += per) {
+        const int fn = nc - f0 < per ? nc - f0 : per;
+        size_t floats = (size_t)fn * frame;
+        // the very last image of the batch may be shorter than the stride (see host_run)
+        if (last_chunk && f0 + fn == nc) floats = ((size_t)(fn - 1) * cfg->image_stride_planes + cfg->channels) * pl.P;
+        CUDA_TRY(cudaMemcpyAsync(img_dev + (size_t)f0 * frame, img_host + (size_t)f0 * frame, floats * sizeof(float),
+                                 cudaMemcpyHostToDevice, g_lane.stream));
+        rc = g_lane.event(&ev);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ev, g_lane.stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+        rc = run_lattice(cfg, pl, false, img_dev, f0, fn, ws, true, st);
+        if (rc) return rc;
+    }
+    rc = run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
+    density_hint_refresh(pl, ws, st);
+    return rc;
+}
+
+// `images_host` != NULL: the frames are there (float32) and `images` is the device buffer they are staged in.
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
                       float *loss, int N, int K, int H, int W, float n_norm, void *workspace, size_t ws_bytes,
-                      cudaStream_t st, int flags = 0)
+                      cudaStream_t st, int flags = 0, const float *images_host = nullptr)
 {
     if (!cfg || !images || !segs || !as_out || !workspace) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     Plan pl;
@@ -1678,8 +1760,14 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
         const int nc = (N - n0) < pl.chunk ? (N - n0) : pl.chunk;
         const char *img = (const char *)images + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem;
         const bool last = n0 + nc >= N;
-        rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,
-                       loss != nullptr, last ? loss : nullptr, n_norm, flags, st);
+        if (images_host)
+            rc = run_chunk_host_frames(cfg, pl, images_host + (size_t)n0 * cfg->image_stride_planes * pl.P,
+                                       (float *)const_cast<char *>(img), segs + (size_t)n0 * K * pl.P,
+                                       as_out + (size_t)n0 * K * pl.P, nc, last, ws, loss != nullptr,
+                                       last ? loss : nullptr, n_norm, flags, st);
+        else
+            rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,
+                           loss != nullptr, last ? loss : nullptr, n_norm, flags, st);
         if (rc) return rc;
     }
     return TCAMCRF_OK;
@@ -2053,6 +2141,18 @@ int tcamcrf_loss_forward(const tcamcrf_config *cfg, const float *images_dev, con
     if (!loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
     return run_filter(cfg, false, images_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
                       workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const float *images_host, float *images_stage_dev,
+                                     const float *segs_dev, float *as_dev, float *loss_dev, int logits, int N, int K,
+                                     int H, int W, float n_norm, void *workspace, size_t workspace_bytes,
+                                     void *cuda_stream)
+{
+    if (!images_host || !images_stage_dev) return fail(TCAMCRF_ERR_INVALID, "null image pointer");
+    if (logits && K < 2) return fail(TCAMCRF_ERR_INVALID, "softmax needs at least two classes");
+    if (logits && !loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
+    return run_filter(cfg, false, images_stage_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
+                      workspace_bytes, (cudaStream_t)cuda_stream, logits ? kFlagLogits : 0, images_host);
 }
 
 int tcamcrf_loss_forward_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, const float *segs_dev,

@@ -55,6 +55,28 @@ def _prep_images(images: torch.Tensor, device: torch.device) -> Tuple[torch.Tens
     return images.contiguous(), u8
 
 
+def _host_frames(images: torch.Tensor, device: torch.device) -> bool:
+    """Frames the trainer left on the CPU (train_wsol.py:1128), in the layout the library copies from directly:
+    float32, contiguous, pinned.  They take tcamcrf_loss_forward_host_frames (the copy overlaps the lattice build)."""
+    return (images.device.type == 'cpu' and device.type == 'cuda' and images.dtype == torch.float32
+            and images.is_contiguous() and images.is_pinned() and images.numel() > 0)
+
+
+_pending_host_frames = []   # (event, tensor): host frames whose asynchronous copy may still be in flight
+
+
+def _keep_until_done(frames: torch.Tensor, device: torch.device) -> None:
+    """torch does not know about the library's copy stream: hold a reference to the pinned tensor until the work
+    queued behind the copy has completed, so the host allocator cannot hand its memory out again meanwhile."""
+    if torch.cuda.is_current_stream_capturing():
+        return   # a captured graph re-reads the tensor on every replay: its owner keeps it alive
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _pending_host_frames.append((ev, frames))
+    while _pending_host_frames and _pending_host_frames[0][0].query():
+        _pending_host_frames.pop(0)
+
+
 def workspace_status(ws: torch.Tensor) -> Tuple[int, int]:
     """(device status bits, vertex count of the last chunk); synchronises the stream."""
     lib = _lib.load()
@@ -85,7 +107,13 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
         segs = segs.float()
     segs = segs.contiguous()
     n, k, h, w = segs.shape
-    images, u8 = _prep_images(images, device)
+    host_frames = images if _host_frames(images, device) else None
+    if host_frames is not None:
+        u8 = False
+        with torch.cuda.device(device):
+            images = torch.empty(host_frames.shape, dtype=torch.float32, device=device)   # staging buffer
+    else:
+        images, u8 = _prep_images(images, device)
     if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
         raise TcamCrfError(f"images {tuple(images.shape)} do not match segmentations {tuple(segs.shape)}")
     if images.shape[1] < cfg.channels:
@@ -100,7 +128,14 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
         ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
         as_out = torch.empty_like(segs)
         stream = _stream_ptr(device)
-        if want_loss:
+        if host_frames is not None:
+            loss = torch.empty(1, dtype=torch.float32, device=device) if want_loss else None
+            rc = lib.tcamcrf_loss_forward_host_frames(
+                byref(cfg), host_frames.data_ptr(), images.data_ptr(), segs.data_ptr(), as_out.data_ptr(),
+                loss.data_ptr() if want_loss else None, 0, n, k, h, w, float(n if n_norm is None else n_norm),
+                ws_ptr, ws_bytes, stream)
+            _keep_until_done(host_frames, device)
+        elif want_loss:
             loss = torch.empty(1, dtype=torch.float32, device=device)
             fn = lib.tcamcrf_loss_forward_u8 if u8 else lib.tcamcrf_loss_forward
             rc = fn(byref(cfg), images.data_ptr(), segs.data_ptr(), as_out.data_ptr(), loss.data_ptr(), n, k, h, w,
@@ -216,7 +251,13 @@ def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Con
     n, k, h, w = logits.shape
     if k < 2:
         raise TcamCrfError("the fused softmax needs at least two classes")
-    images, u8 = _prep_images(images, device)
+    host_frames = images if _host_frames(images, device) else None
+    if host_frames is not None:
+        u8 = False
+        with torch.cuda.device(device):
+            images = torch.empty(host_frames.shape, dtype=torch.float32, device=device)   # staging buffer
+    else:
+        images, u8 = _prep_images(images, device)
     if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
         raise TcamCrfError(f"images {tuple(images.shape)} do not match logits {tuple(logits.shape)}")
     if images.shape[1] < cfg.channels:
@@ -231,10 +272,17 @@ def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Con
         ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
         as_out = torch.empty_like(logits)
         loss = torch.empty(1, dtype=torch.float32, device=device)
-        rc = lib.tcamcrf_loss_forward_logits(byref(cfg), images.data_ptr(), 1 if u8 else 0, logits.data_ptr(),
-                                             as_out.data_ptr(), loss.data_ptr(), n, k, h, w,
-                                             float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
-                                             _stream_ptr(device))
+        if host_frames is not None:
+            rc = lib.tcamcrf_loss_forward_host_frames(
+                byref(cfg), host_frames.data_ptr(), images.data_ptr(), logits.data_ptr(), as_out.data_ptr(),
+                loss.data_ptr(), 1, n, k, h, w, float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
+                _stream_ptr(device))
+            _keep_until_done(host_frames, device)
+        else:
+            rc = lib.tcamcrf_loss_forward_logits(byref(cfg), images.data_ptr(), 1 if u8 else 0, logits.data_ptr(),
+                                                 as_out.data_ptr(), loss.data_ptr(), n, k, h, w,
+                                                 float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
+                                                 _stream_ptr(device))
         _lib.check(rc, "tcamcrf_loss_forward_logits")
         if STRICT if check is None else check:
             _raise_on_status(ws if ws_ptr == ws.data_ptr() else ws[ws_ptr - ws.data_ptr():])

@@ -248,6 +248,49 @@ def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, monkeypatch, n, gro
     assert rel_err(grad, want_grad) < REL_TOL
 
 
+@pytest.mark.parametrize("n,sections", [(32, None), (5, None), (70, None), (9, "1"), (13, "64"), (1, None)])
+def test_host_frames_path(torch_cuda, oracle_mod, monkeypatch, n, sections):
+    """Frames left on the CPU in pinned memory (what the reference's trainer passes) take
+    tcamcrf_loss_forward_host_frames: copied section by section on the library's copy stream while the lattice of
+    the sections already in is built.  Same AS / loss as the oracle, for one and several chunks, ragged sections,
+    the filter-only and the fused-softmax variants; pageable frames take the plain copy."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    if sections is None:
+        monkeypatch.delenv("TCAMCRF_HIMG_SECTIONS", raising=False)
+    else:
+        monkeypatch.setenv("TCAMCRF_HIMG_SECTIONS", sections)
+    k, h, w = 3, 24, 20
+    img = synth.make_images(n, h, w, "noise" if n % 2 else "natural", seed=90 + n)
+    seg_np = synth.make_segs(n, k, h, w, seed=90 + n)
+    seg = torch.from_numpy(seg_np).cuda()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    want_loss, _, want_as = oracle_mod.densecrf_loss_fwd_bwd(img, seg_np, 15.0, 100.0, 1.0,
+                                                             oracle_mod.port_bilateralfilter_batch)
+    pinned = torch.from_numpy(img).pin_memory()
+    assert ops._host_frames(pinned, seg.device) and not ops._host_frames(torch.from_numpy(img), seg.device)
+    lib = _lib.load()
+    for rep in range(3):     # the staging buffer and the copy lane are reused from call to call
+        l0 = lib.tcamcrf_launch_count()
+        got, loss, _ = ops.crf_forward(pinned, seg, cfg, check=True)
+        launches = lib.tcamcrf_launch_count() - l0
+        _assert_close(got.cpu().numpy(), want_as, f"AS, host frames, call {rep}")
+        assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
+    l0 = lib.tcamcrf_launch_count()
+    got_dev, _, _ = ops.crf_forward(torch.from_numpy(img), seg, cfg, check=True)     # pageable: plain copy, one section
+    torch.cuda.synchronize()
+    if n > 4 and sections != "1":
+        assert launches > lib.tcamcrf_launch_count() - l0      # the lattice stages really ran section by section
+    assert rel_err(got.cpu().numpy(), got_dev.cpu().numpy()) < 1e-5
+    got, loss = ops.crf_forward(pinned, seg, cfg, want_loss=False, check=True)[:2]
+    assert loss is None
+    _assert_close(got.cpu().numpy(), want_as, "AS, host frames, filter only")
+    logits = torch.from_numpy(np.log(seg_np)).cuda()       # softmax(log p) = p
+    got, loss, _ = ops.crf_forward_logits(pinned, logits, cfg, check=True)
+    _assert_close(got.cpu().numpy(), want_as, "AS, host frames, fused softmax")
+    assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
+
+
 def test_u8_images_and_chunking_give_identical_results(torch_cuda):
     """uint8 images produce the same features as float images holding the same integers, and processing the
     batch in chunks of frames does not change anything but the summation order inside the loss."""
