@@ -18,6 +18,7 @@ import argparse
 import ctypes
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -170,6 +171,46 @@ def cpu_fwd_bwd_frames_per_sec(frames: int, K: int, kind: str, reps: int, warmup
         if i >= warmup:
             times.append(dt)
     return frames / min(times), frames / (sum(times) / len(times)), which, threads, cores, times
+
+
+def cpu_context_runs(K: int, kind: str):
+    """SURVEY 8d's two other CPU arms, as context next to the all-cores number: (i) one thread, (iii) all cores with
+    glibc malloc kept from returning the per-class buffers to the OS (the reference allocates and frees two
+    [H*W] float arrays per class, bilateralfilter.cpp:31-37).  Small samples; (iii) needs the environment set
+    before the process starts, so it runs in a child."""
+    out = {}
+    try:
+        import oracle
+        if not oracle.have_ref():
+            return out
+        cores = len(os.sched_getaffinity(0))
+        fn, _ = oracle.best_filter(color=False)
+        from tcam_wsol_video_b200 import synth
+        img = synth.make_images(2, H, W, kind, seed=0)
+        seg = synth.make_segs(2, K, H, W, seed=0)
+        oracle.ref_set_threads(1)
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            oracle.densecrf_loss_fwd_bwd(img, seg, SIGMA_RGB, SIGMA_XY, 1.0, fn)
+            best = min(best, time.perf_counter() - t0)
+        oracle.ref_set_threads(cores)
+        out["one_thread"] = {"value": 2 / best, "unit": UNIT, "cores": 1, "sample": "2 frames, best of 2"}
+        env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="1073741824", MALLOC_TRIM_THRESHOLD_="1073741824",
+                   MALLOC_TOP_PAD_="268435456", OMP_NUM_THREADS=str(cores))
+        code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+                "b, m, which, threads, cores, t = bench.cpu_fwd_bwd_frames_per_sec(%d, %d, %r, reps=2, warmup=1)\n"
+                "print('MALLOC_TUNED', b, threads)" % (ROOT, min(32, max(cores, 2)), K, kind))
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        for ln in res.stdout.splitlines():
+            if ln.startswith("MALLOC_TUNED"):
+                _, v, th = ln.split()
+                out["malloc_tuned"] = {"value": float(v), "unit": UNIT, "cores": int(th),
+                                       "sample": f"{min(32, max(cores, 2))} frames, best of 2 after 1 warm-up, "
+                                                 "MALLOC_MMAP_THRESHOLD_/TRIM_THRESHOLD_=1 GiB, TOP_PAD_=256 MiB"}
+    except Exception as exc:   # context only: never fail the bench line over it
+        out["error"] = repr(exc)[:200]
+    return out
 
 
 def run_reference(args, rank: int, world: int):
@@ -499,7 +540,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         best, mean, which, threads, cores, times = cpu_fwd_bwd_frames_per_sec(frames, K, args.kind, reps=3, warmup=1)
         cpu = {"value": best, "unit": UNIT, "cores": threads, "kind": which, "host_cores": cores,
                "sample": f"{frames} frames x K={K} x {H}x{W} ({args.kind}), fwd+bwd, best of 3 after 1 warm-up, "
-                         f"OpenMP over frames as shipped", "mean_value": mean}
+                         f"OpenMP over frames as shipped", "mean_value": mean,
+               "context": cpu_context_runs(K, args.kind)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
