@@ -1584,6 +1584,7 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
     pp.frame0 = frame0;
     // dense lattice lately (more than one vertex per four pixels in the fullest frame): row-cooperative splat
     pp.dense = (long long)density_hint(ws) * 4 > (long long)pl.P ? 1 : 0;
+    if (const char *env = getenv("TCAMCRF_DENSE")) pp.dense = atoi(env) != 0;   // tests and sweeps: force either way
     pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
     {

@@ -431,6 +431,42 @@ def test_adaptive_table_size_follows_the_frames(torch_cuda, oracle_mod, k):
         assert sizes[4] == sizes[3] and sizes[5] < sizes[3], sizes     # call 4 still sized by the noise call 3
 
 
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+@pytest.mark.parametrize("k,dim,hw", [(10, 0, (40, 52)), (5, 0, (33, 35)), (7, 0, (24, 130)), (12, 0, (31, 37)),
+                                      (16, 0, (40, 40)), (13, 3, (40, 44)), (9, 0, (1, 50))])
+def test_row_cooperative_kernels(torch_cuda, oracle_mod, monkeypatch, kind, k, dim, hw):
+    """splat_rows_kernel / slice_rows_kernel (the kernels the density hint selects for dense lattices, K = 5..16:
+    neighbouring lanes share a vertex row) forced on with TCAMCRF_DENSE=1, against the oracle and against the
+    per-pixel kernels (TCAMCRF_DENSE=0): every row width (2, 3, 4 float4s), ragged frames (pixel counts that are
+    not multiples of 32), 5-D and colour lattices, probabilities and the fused softmax."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    h, w = hw
+    n = 3
+    img = synth.make_images(n, h, w, kind, seed=k)
+    seg_np = synth.make_segs(n, k, h, w, seed=k)
+    seg = torch.from_numpy(seg_np).cuda()
+    logits = torch.from_numpy(np.log(seg_np)).cuda()       # softmax(log p) = p
+    if dim:
+        cfg = _lib.make_config(_lib.FEAT_COLOR, dim, 15.0)
+        want = oracle_mod.port_colorbilateralfilter_batch(img, seg_np, n, k, h, w, 15.0, dim).reshape(seg_np.shape)
+    else:
+        cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+        want = oracle_mod.port_bilateralfilter_batch(img, seg_np, n, k, h, w, 15.0, 100.0).reshape(seg_np.shape)
+    want_loss = -(seg_np.astype(np.float64) * want.astype(np.float64)).sum() / n
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TCAMCRF_DENSE", mode)
+        got, loss, _ = ops.crf_forward(torch.from_numpy(img), seg, cfg, check=True)
+        _assert_close(got.cpu().numpy(), want, f"AS, TCAMCRF_DENSE={mode}")
+        assert abs(loss.item() - want_loss) < REL_TOL * abs(want_loss)
+        out[mode] = got
+        got, loss, _ = ops.crf_forward_logits(torch.from_numpy(img), logits, cfg, check=True)
+        _assert_close(got.cpu().numpy(), want, f"AS from logits, TCAMCRF_DENSE={mode}")
+        assert abs(loss.item() - want_loss) < REL_TOL * abs(want_loss)
+    assert rel_err(out["1"].cpu().numpy(), out["0"].cpu().numpy()) < 1e-5
+
+
 def test_full_size_properties_config2(torch_cuda):
     """BASELINE configs[1] at full size (32 x 10 classes x 224^2): too slow for the scalar oracle in a unit
     test, so check size-independent properties: linearity, channel independence (K=10 in one pass equals
