@@ -1466,16 +1466,21 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
 #define TCAMCRF_DENSITY_HINT 1
 #endif
 struct DensityHints {
+    struct Slot {
+        void *ws;
+        int *word;            // pinned
+        unsigned int calls;   // calls seen on this workspace
+    };
     std::mutex mu;
-    std::vector<std::pair<void *, int *>> slots;   // workspace -> pinned word (a handful of workspaces per process)
+    std::vector<Slot> slots;   // a handful of workspaces per process
     cudaStream_t side = nullptr;                   // the copies run here, off the caller's stream
     cudaEvent_t ev = nullptr;
     int device = -1;
-    int *find(void *ws, bool create)
+    // caller holds `mu`
+    Slot *find(void *ws, bool create)
     {
-        std::lock_guard<std::mutex> lock(mu);
         for (auto &s : slots)
-            if (s.first == ws) return s.second;
+            if (s.ws == ws) return &s;
         if (!create) return nullptr;
         int *p = nullptr;
         if (cudaHostAlloc((void **)&p, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
@@ -1483,8 +1488,8 @@ struct DensityHints {
             return nullptr;
         }
         *p = 0;
-        slots.emplace_back(ws, p);
-        return p;
+        slots.push_back({ws, p, 0u});
+        return &slots.back();
     }
 };
 static DensityHints g_hints;
@@ -1503,8 +1508,9 @@ static bool stream_is_capturing(cudaStream_t st)
 static int density_hint(void *ws)
 {
     if (!TCAMCRF_DENSITY_HINT) return 0;
-    int *slot = g_hints.find(ws, false);
-    return slot ? *(volatile int *)slot : 0;
+    std::lock_guard<std::mutex> lock(g_hints.mu);
+    DensityHints::Slot *slot = g_hints.find(ws, false);
+    return slot ? *(volatile int *)slot->word : 0;
 }
 
 // Queue the refresh of the hint behind the work already on `st`, on a side stream: the caller's stream never waits
@@ -1513,15 +1519,14 @@ static int density_hint(void *ws)
 static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
 {
     if (!TCAMCRF_DENSITY_HINT) return;
+    std::lock_guard<std::mutex> lock(g_hints.mu);
+    DensityHints::Slot *slot = g_hints.find(ws, true);
+    if (!slot) return;
     // every 8th call is plenty for a hint (the three driver calls below cost ~10 us of host time, which shows on
     // 0.25 ms steps); the first two calls on a workspace always refresh
-    static thread_local unsigned int calls = 0;
-    const unsigned int c = calls++;
+    const unsigned int c = slot->calls++;
     if (c >= 2 && (c & 7u) != 0) return;
     if (stream_is_capturing(st)) return;
-    int *slot = g_hints.find(ws, true);
-    if (!slot) return;
-    std::lock_guard<std::mutex> lock(g_hints.mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     if (g_hints.device != dev || !g_hints.side) {   // one process drives one GPU; re-create if that ever changes
@@ -1535,7 +1540,7 @@ static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
     }
     cudaEventRecord(g_hints.ev, st);
     cudaStreamWaitEvent(g_hints.side, g_hints.ev, 0);
-    cudaMemcpyAsync(slot, ws + pl.off_ctrl + kCtrlPrevMax * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost,
+    cudaMemcpyAsync(slot->word, ws + pl.off_ctrl + kCtrlPrevMax * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost,
                     g_hints.side);
 }
 
