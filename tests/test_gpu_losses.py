@@ -236,23 +236,28 @@ def test_dense_crf_filter_mean_field(torch_cuda, oracle_mod, shape, quirk):
     assert torch.equal(same, seg)
 
 
-def test_module_matches_the_reference_autograd_function(torch_cuda):
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable-frames", "pinned-frames"])
+def test_module_matches_the_reference_autograd_function(torch_cuda, pinned):
     """DenseCRFLoss (CUDA) against loss and gradient produced by the reference's own DenseCRFLossFunction executed on
-    CPU tensors with the reference's C++ behind it (tests/golden/py/py_dense_crf_loss.npz)."""
+    CPU tensors with the reference's C++ behind it (tests/golden/py/py_dense_crf_loss.npz).  The frames stay on the
+    CPU as in the reference's trainer; pinned ones take tcamcrf_loss_forward_host_frames."""
     import os
     torch = torch_cuda
     from conftest import GOLDEN
     from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
     g = np.load(os.path.join(GOLDEN, "py", "py_dense_crf_loss.npz"))
     seg = torch.from_numpy(g["seg"]).cuda().requires_grad_(True)
-    loss = DenseCRFLoss(float(g["weight"]), 15.0, 100.0, 1.0)(images=torch.from_numpy(g["image"]), segmentations=seg)
+    image = torch.from_numpy(g["image"])
+    loss = DenseCRFLoss(float(g["weight"]), 15.0, 100.0, 1.0)(images=image.pin_memory() if pinned else image,
+                                                              segmentations=seg)
     loss.backward()
     assert loss.shape == (1,)
     assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
     assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL
 
 
-def test_colour_module_matches_the_reference_autograd_function(torch_cuda):
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable-frames", "pinned-frames"])
+def test_colour_module_matches_the_reference_autograd_function(torch_cuda, pinned):
     """ColorDenseCRFLoss (CUDA) against the reference's own ColorDenseCRFLossFunction executed on CPU tensors."""
     import os
     torch = torch_cuda
@@ -260,7 +265,9 @@ def test_colour_module_matches_the_reference_autograd_function(torch_cuda):
     from tcam_wsol_video_b200.color_dense_crf_loss import ColorDenseCRFLoss
     g = np.load(os.path.join(GOLDEN, "py", "py_color_dense_crf_loss.npz"))
     seg = torch.from_numpy(g["seg"]).cuda().requires_grad_(True)
-    loss = ColorDenseCRFLoss(float(g["weight"]), 15.0, 1.0)(images=torch.from_numpy(g["image"]), segmentations=seg)
+    image = torch.from_numpy(g["image"])
+    loss = ColorDenseCRFLoss(float(g["weight"]), 15.0, 1.0)(images=image.pin_memory() if pinned else image,
+                                                            segmentations=seg)
     loss.backward()
     assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
     assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL
