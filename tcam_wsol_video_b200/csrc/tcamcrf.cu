@@ -1704,8 +1704,8 @@ static CopyLane g_lane;
 
 // One chunk whose frames come from the host: `img_host` / `img_dev` point at frame 0 of the chunk.
 static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, const float *img_host, float *img_dev,
-                                 const float *segs, float *as_out, int nc, bool last_chunk, char *ws, bool want_loss,
-                                 float *loss_final, float n_norm, int flags, cudaStream_t st)
+                                 const float *segs, float *as_out, int nc, bool first_chunk, bool last_chunk, char *ws,
+                                 bool want_loss, float *loss_final, float n_norm, int flags, cudaStream_t st)
 {
     // sections of at least 4 frames, 4 per chunk by default (32 frames: 8 + 8 + 8 + 8)
     int nsec = 4;
@@ -1720,11 +1720,14 @@ static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, cons
     int rc = g_lane.ready();
     if (rc) return rc;
     cudaEvent_t ev;
-    rc = g_lane.event(&ev);
-    if (rc) return rc;
-    // the staging buffer may still be read by work queued earlier on the caller's stream
-    CUDA_TRY(cudaEventRecord(ev, st));
-    CUDA_TRY(cudaStreamWaitEvent(g_lane.stream, ev, 0));
+    if (first_chunk) {
+        // the staging buffer may still be read by work queued earlier on the caller's stream; later chunks of the
+        // call use other parts of it, and their copies simply queue behind the first chunk's on the copy stream
+        rc = g_lane.event(&ev);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(g_lane.stream, ev, 0));
+    }
     for (int f0 = 0; f0 < nc; f0 += per) {
         const int fn = nc - f0 < per ? nc - f0 : per;
         size_t floats = (size_t)fn * frame;
@@ -1769,7 +1772,7 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
         if (images_host)
             rc = run_chunk_host_frames(cfg, pl, images_host + (size_t)n0 * cfg->image_stride_planes * pl.P,
                                        (float *)const_cast<char *>(img), segs + (size_t)n0 * K * pl.P,
-                                       as_out + (size_t)n0 * K * pl.P, nc, last, ws, loss != nullptr,
+                                       as_out + (size_t)n0 * K * pl.P, nc, n0 == 0, last, ws, loss != nullptr,
                                        last ? loss : nullptr, n_norm, flags, st);
         else
             rc = run_chunk(cfg, pl, u8, img, segs + (size_t)n0 * K * pl.P, as_out + (size_t)n0 * K * pl.P, nc, ws,

@@ -530,6 +530,41 @@ def test_cuda_graph_capture_and_replay(torch_cuda, oracle_mod):
         assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
 
 
+def test_cuda_graph_capture_with_host_frames(torch_cuda, oracle_mod):
+    """The host-frames forward only forks to the library's copy stream and joins back with events, so it can be
+    captured too: the graph then re-reads the pinned frames on every replay."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    n, k, h, w = 6, 2, 40, 36
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    frames = torch.zeros((n, 3, h, w)).pin_memory()
+    seg = torch.zeros((n, k, h, w), device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        frames.copy_(torch.from_numpy(synth.make_images(n, h, w, "natural", seed=5)))
+        seg.copy_(torch.from_numpy(synth.make_segs(n, k, h, w, seed=5)))
+        for _ in range(2):                              # warm-up on the capture stream (workspace, copy lane)
+            as_t, loss, _ = ops.crf_forward(frames, seg, cfg)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        as_t, loss, _ = ops.crf_forward(frames, seg, cfg)
+    for seed, kind in ((6, "noise"), (7, "natural")):
+        img_np = synth.make_images(n, h, w, kind, seed=seed)
+        seg_np = synth.make_segs(n, k, h, w, seed=seed)
+        frames.copy_(torch.from_numpy(img_np))          # host-side write: the replay below picks it up
+        seg.copy_(torch.from_numpy(seg_np))
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        want_loss, _, want_as = oracle_mod.densecrf_loss_fwd_bwd(img_np, seg_np, 15.0, 100.0, 1.0,
+                                                                 oracle_mod.port_bilateralfilter_batch)
+        _assert_close(as_t.cpu().numpy(), want_as, f"graph AS, host frames, {kind}")
+        assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
+
+
 def test_temporal_max_bit_exact(torch_cuda):
     torch = torch_cuda
     from tcam_wsol_video_b200 import ops
