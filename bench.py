@@ -529,6 +529,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                  "achieved": frame_bytes(P, D, K, M) * value / world / 1e9,
                                  "frac": frame_bytes(P, D, K, M) * value / world / 1e9 / peak},
                     "stages": stages}
+        if traffic and stages[dom]["ms_per_launch"] > 0:
+            # the same launch against the DRAM bytes ncu measured for it: what the HBM really carried
+            dram_gbs = traffic / (stages[dom]["ms_per_launch"] * 1e-3) / 1e9
+            roofline["dram"] = {"achieved": dram_gbs, "frac": dram_gbs / peak, "unit": "GB/s",
+                                "what": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (`traffic`) over "
+                                        "the live per-launch time"}
         if roofline["frac"] > 1.0:
             roofline["note"] = ("frac > 1: SURVEY 8d's algorithmic bytes of this stage count the neighbour-row gathers, "
                                 "which the L2 serves; `traffic` is the DRAM traffic per launch (ncu), "
