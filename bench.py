@@ -398,6 +398,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                "api": "DenseCRFLoss(images=pinned host float32, segmentations=device).backward(); "
                                       "loss.item()"}
 
+        # the same call with uint8 frames from the loader: a quarter of the bytes on the wire
+        img8_h = [(s[0].to(torch.uint8)).pin_memory() for s in sets]
+
+        def module_step_u8(i):
+            seg_d = sets[i % len(sets)][3]
+            seg_d.grad = None
+            loss = crf(images=img8_h[i % len(sets)], segmentations=seg_d)
+            loss.backward()
+            return loss.item()
+
+        for i in range(3):
+            module_step_u8(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            module_step_u8(i)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        t = torch.tensor([dtm], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dtm = float(t.item())
+        e2e["trainer_call_u8"] = {"value": world * N * e2e_steps / dtm, "unit": UNIT, "ms_per_step": 1e3 * dtm / e2e_steps,
+                                  "h2d_bytes_per_step": int(N * 3 * P), "d2h_bytes_per_step": 4,
+                                  "api": "DenseCRFLoss(images=pinned host uint8, segmentations=device).backward(); "
+                                         "loss.item()"}
+
     # ---- the same step on the other input regimes (short, device-resident; context for the headline number)
     extra = {}
     if world == 1 and not args.no_extra:

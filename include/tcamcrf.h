@@ -129,16 +129,16 @@ int tcamcrf_loss_forward_u8(const tcamcrf_config *cfg, const uint8_t *images_dev
 /* tcamcrf_loss_forward (loss_dev != NULL) / tcamcrf_filter (loss_dev == NULL) for frames that are still in HOST
  * memory -- what the reference's trainer passes: raw_img stays on the CPU (dlib/learning/train_wsol.py:1128) and
  * DenseCRFLossFunction.forward receives it every step (dlib/crf/dense_crf_loss.py:36-49).  images_host
- * [N, stride_planes, H, W] float32 (pinned for a truly asynchronous copy; pageable memory works, the driver then
- * stages it) is copied into images_stage_dev (same size, device) section by section on a copy stream of the
+ * [N, stride_planes, H, W] float32, or uint8 when images_u8 != 0 (a quarter of the bytes: SURVEY.md 8(f).1), pinned
+ * for a truly asynchronous copy (pageable memory works, the driver then stages it), is copied into images_stage_dev (same size, device) section by section on a copy stream of the
  * library, and the lattice of every section is built on cuda_stream as soon as its frames are in: the copy hides
  * behind the lattice build instead of preceding it.  Stream-ordered (events only, no synchronisation): the call
  * returns once everything is queued, and images_host must stay untouched until cuda_stream has passed this call.
  * logits != 0: segs_dev holds logits (see tcamcrf_loss_forward_logits below). */
-int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const float *images_host, float *images_stage_dev,
-                                     const float *segs_dev, float *as_dev, float *loss_dev, int logits, int N, int K,
-                                     int H, int W, float n_norm, void *workspace, size_t workspace_bytes,
-                                     void *cuda_stream);
+int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const void *images_host, void *images_stage_dev,
+                                     int images_u8, const float *segs_dev, float *as_dev, float *loss_dev, int logits,
+                                     int N, int K, int H, int W, float n_norm, void *workspace,
+                                     size_t workspace_bytes, void *cuda_stream);
 
 /* Backward: grad_seg = ((-2 * grad_out[0]) * AS) / n_norm, the reference's expression and rounding
  * order (dlib/crf/dense_crf_loss.py:73).  count = N*K*H*W. */

@@ -1703,9 +1703,10 @@ struct CopyLane {
 static CopyLane g_lane;
 
 // One chunk whose frames come from the host: `img_host` / `img_dev` point at frame 0 of the chunk.
-static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, const float *img_host, float *img_dev,
-                                 const float *segs, float *as_out, int nc, bool first_chunk, bool last_chunk, char *ws,
-                                 bool want_loss, float *loss_final, float n_norm, int flags, cudaStream_t st)
+static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, bool u8, const char *img_host,
+                                 char *img_dev, const float *segs, float *as_out, int nc, bool first_chunk,
+                                 bool last_chunk, char *ws, bool want_loss, float *loss_final, float n_norm, int flags,
+                                 cudaStream_t st)
 {
     // sections of at least 4 frames, 4 per chunk by default (32 frames: 8 + 8 + 8 + 8)
     int nsec = 4;
@@ -1715,7 +1716,8 @@ static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, cons
     }
     int per = (nc + nsec - 1) / nsec;
     if (per < 4) per = nc < 4 ? nc : 4;
-    const size_t frame = (size_t)cfg->image_stride_planes * pl.P;   // floats per image
+    const size_t elem = u8 ? 1 : sizeof(float);
+    const size_t frame = (size_t)cfg->image_stride_planes * pl.P;   // elements per image
     std::lock_guard<std::mutex> lock(g_lane.mu);
     int rc = g_lane.ready();
     if (rc) return rc;
@@ -1730,16 +1732,16 @@ static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, cons
     }
     for (int f0 = 0; f0 < nc; f0 += per) {
         const int fn = nc - f0 < per ? nc - f0 : per;
-        size_t floats = (size_t)fn * frame;
+        size_t elems = (size_t)fn * frame;
         // the very last image of the batch may be shorter than the stride (see host_run)
-        if (last_chunk && f0 + fn == nc) floats = ((size_t)(fn - 1) * cfg->image_stride_planes + cfg->channels) * pl.P;
-        CUDA_TRY(cudaMemcpyAsync(img_dev + (size_t)f0 * frame, img_host + (size_t)f0 * frame, floats * sizeof(float),
+        if (last_chunk && f0 + fn == nc) elems = ((size_t)(fn - 1) * cfg->image_stride_planes + cfg->channels) * pl.P;
+        CUDA_TRY(cudaMemcpyAsync(img_dev + (size_t)f0 * frame * elem, img_host + (size_t)f0 * frame * elem, elems * elem,
                                  cudaMemcpyHostToDevice, g_lane.stream));
         rc = g_lane.event(&ev);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(ev, g_lane.stream));
         CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
-        rc = run_lattice(cfg, pl, false, img_dev, f0, fn, ws, true, st);
+        rc = run_lattice(cfg, pl, u8, img_dev, f0, fn, ws, true, st);
         if (rc) return rc;
     }
     rc = run_values(pl, segs, as_out, 0, nc, ws, false, want_loss, loss_final, n_norm, flags, st);
@@ -1747,10 +1749,11 @@ static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, cons
     return rc;
 }
 
-// `images_host` != NULL: the frames are there (float32) and `images` is the device buffer they are staged in.
+// `images_host` != NULL: the frames are there (same element type) and `images` is the device buffer they are
+// staged in.
 static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, const float *segs, float *as_out,
                       float *loss, int N, int K, int H, int W, float n_norm, void *workspace, size_t ws_bytes,
-                      cudaStream_t st, int flags = 0, const float *images_host = nullptr)
+                      cudaStream_t st, int flags = 0, const void *images_host = nullptr)
 {
     if (!cfg || !images || !segs || !as_out || !workspace) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     Plan pl;
@@ -1770,8 +1773,9 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
         const char *img = (const char *)images + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem;
         const bool last = n0 + nc >= N;
         if (images_host)
-            rc = run_chunk_host_frames(cfg, pl, images_host + (size_t)n0 * cfg->image_stride_planes * pl.P,
-                                       (float *)const_cast<char *>(img), segs + (size_t)n0 * K * pl.P,
+            rc = run_chunk_host_frames(cfg, pl, u8,
+                                       (const char *)images_host + (size_t)n0 * cfg->image_stride_planes * pl.P * img_elem,
+                                       const_cast<char *>(img), segs + (size_t)n0 * K * pl.P,
                                        as_out + (size_t)n0 * K * pl.P, nc, n0 == 0, last, ws, loss != nullptr,
                                        last ? loss : nullptr, n_norm, flags, st);
         else
@@ -2152,15 +2156,15 @@ int tcamcrf_loss_forward(const tcamcrf_config *cfg, const float *images_dev, con
                       workspace_bytes, (cudaStream_t)cuda_stream);
 }
 
-int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const float *images_host, float *images_stage_dev,
-                                     const float *segs_dev, float *as_dev, float *loss_dev, int logits, int N, int K,
-                                     int H, int W, float n_norm, void *workspace, size_t workspace_bytes,
-                                     void *cuda_stream)
+int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const void *images_host, void *images_stage_dev,
+                                     int images_u8, const float *segs_dev, float *as_dev, float *loss_dev, int logits,
+                                     int N, int K, int H, int W, float n_norm, void *workspace,
+                                     size_t workspace_bytes, void *cuda_stream)
 {
     if (!images_host || !images_stage_dev) return fail(TCAMCRF_ERR_INVALID, "null image pointer");
     if (logits && K < 2) return fail(TCAMCRF_ERR_INVALID, "softmax needs at least two classes");
     if (logits && !loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
-    return run_filter(cfg, false, images_stage_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
+    return run_filter(cfg, images_u8 != 0, images_stage_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
                       workspace_bytes, (cudaStream_t)cuda_stream, logits ? kFlagLogits : 0, images_host);
 }
 

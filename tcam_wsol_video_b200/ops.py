@@ -57,8 +57,8 @@ def _prep_images(images: torch.Tensor, device: torch.device) -> Tuple[torch.Tens
 
 def _host_frames(images: torch.Tensor, device: torch.device) -> bool:
     """Frames the trainer left on the CPU (train_wsol.py:1128), in the layout the library copies from directly:
-    float32, contiguous, pinned.  They take tcamcrf_loss_forward_host_frames (the copy overlaps the lattice build)."""
-    return (images.device.type == 'cpu' and device.type == 'cuda' and images.dtype == torch.float32
+    float32 (or uint8), contiguous, pinned.  They take tcamcrf_loss_forward_host_frames (the copy overlaps the lattice build)."""
+    return (images.device.type == 'cpu' and device.type == 'cuda' and images.dtype in (torch.float32, torch.uint8)
             and images.is_contiguous() and images.is_pinned() and images.numel() > 0)
 
 
@@ -109,9 +109,9 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
     n, k, h, w = segs.shape
     host_frames = images if _host_frames(images, device) else None
     if host_frames is not None:
-        u8 = False
+        u8 = host_frames.dtype == torch.uint8
         with torch.cuda.device(device):
-            images = torch.empty(host_frames.shape, dtype=torch.float32, device=device)   # staging buffer
+            images = torch.empty(host_frames.shape, dtype=host_frames.dtype, device=device)   # staging buffer
     else:
         images, u8 = _prep_images(images, device)
     if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
@@ -131,8 +131,8 @@ def crf_forward(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Config, want
         if host_frames is not None:
             loss = torch.empty(1, dtype=torch.float32, device=device) if want_loss else None
             rc = lib.tcamcrf_loss_forward_host_frames(
-                byref(cfg), host_frames.data_ptr(), images.data_ptr(), segs.data_ptr(), as_out.data_ptr(),
-                loss.data_ptr() if want_loss else None, 0, n, k, h, w, float(n if n_norm is None else n_norm),
+                byref(cfg), host_frames.data_ptr(), images.data_ptr(), 1 if u8 else 0, segs.data_ptr(),
+                as_out.data_ptr(), loss.data_ptr() if want_loss else None, 0, n, k, h, w, float(n if n_norm is None else n_norm),
                 ws_ptr, ws_bytes, stream)
             _keep_until_done(host_frames, device)
         elif want_loss:
@@ -253,9 +253,9 @@ def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Con
         raise TcamCrfError("the fused softmax needs at least two classes")
     host_frames = images if _host_frames(images, device) else None
     if host_frames is not None:
-        u8 = False
+        u8 = host_frames.dtype == torch.uint8
         with torch.cuda.device(device):
-            images = torch.empty(host_frames.shape, dtype=torch.float32, device=device)   # staging buffer
+            images = torch.empty(host_frames.shape, dtype=host_frames.dtype, device=device)   # staging buffer
     else:
         images, u8 = _prep_images(images, device)
     if images.ndim != 4 or images.shape[0] != n or tuple(images.shape[2:]) != (h, w):
@@ -274,8 +274,8 @@ def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Con
         loss = torch.empty(1, dtype=torch.float32, device=device)
         if host_frames is not None:
             rc = lib.tcamcrf_loss_forward_host_frames(
-                byref(cfg), host_frames.data_ptr(), images.data_ptr(), logits.data_ptr(), as_out.data_ptr(),
-                loss.data_ptr(), 1, n, k, h, w, float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
+                byref(cfg), host_frames.data_ptr(), images.data_ptr(), 1 if u8 else 0, logits.data_ptr(),
+                as_out.data_ptr(), loss.data_ptr(), 1, n, k, h, w, float(n if n_norm is None else n_norm), ws_ptr, ws_bytes,
                 _stream_ptr(device))
             _keep_until_done(host_frames, device)
         else:

@@ -282,6 +282,12 @@ def test_host_frames_path(torch_cuda, oracle_mod, monkeypatch, n, sections):
     if n > 4 and sections != "1":
         assert launches > lib.tcamcrf_launch_count() - l0      # the lattice stages really ran section by section
     assert rel_err(got.cpu().numpy(), got_dev.cpu().numpy()) < 1e-5
+    # uint8 frames from the loader (a quarter of the bytes on the wire): identical features
+    pinned8 = torch.from_numpy(img.astype(np.uint8)).pin_memory()
+    assert ops._host_frames(pinned8, seg.device)
+    got8, loss8, _ = ops.crf_forward(pinned8, seg, cfg, check=True)
+    _assert_close(got8.cpu().numpy(), want_as, "AS, uint8 host frames")
+    assert abs(loss8.item() - float(want_loss)) < REL_TOL * abs(float(want_loss))
     got, loss = ops.crf_forward(pinned, seg, cfg, want_loss=False, check=True)[:2]
     assert loss is None
     _assert_close(got.cpu().numpy(), want_as, "AS, host frames, filter only")

@@ -14,5 +14,5 @@ python - <<'PY'
 import json
 for f in ['v9_bench','v9_natural_bench','v9_k2_bench','v9_natural_k2_bench']:
     d = json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
-    print(f, round(d['value']), round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'trainer', round(d['e2e']['trainer_call']['value']), 'cpu', d['cpu_baseline'] and (round(d['cpu_baseline']['value'],1), d['cpu_baseline'].get('context')))
+    print(f, round(d["value"]), round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]), "trainer", round(d["e2e"]["trainer_call"]["value"]), "trainer_u8", round(d["e2e"]["trainer_call_u8"]["value"]), 'cpu', d['cpu_baseline'] and (round(d['cpu_baseline']['value'],1), d['cpu_baseline'].get('context')))
 PY
