@@ -70,7 +70,8 @@ typedef struct tcamcrf_config {
     float hash_load;   /* load factor the primary table tier would have at 1.2 vertices per pixel; 0 -> default (0.25).
                           Larger lattices spill into a worst-case-sized overflow tier, so any value is safe. */
     float pool_factor; /* vertex pool size as a fraction of the worst case (d+1)*H*W per frame; 0 -> 1.0 */
-    int chunk_frames;  /* frames processed per pass (bounds the workspace); 0 -> default (64) */
+    int chunk_frames;  /* frames processed per pass (bounds the workspace); 0 -> default: 64, fewer for large frames
+                          (workspace kept within ~16 GiB).  Always lowered when 32-bit vertex / entry indices need it. */
 } tcamcrf_config;
 
 int tcamcrf_version(void);
@@ -101,6 +102,11 @@ int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, cons
 int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev, int images_u8, const float *segs_dev,
                                float *ats_dev, int N, int K, int H, int W, void *workspace, size_t workspace_bytes,
                                void *cuda_stream);
+
+/* Frames one pass works on for this problem (what tcamcrf_workspace_bytes sizes the workspace for): cfg->chunk_frames
+ * or the default 64, capped by N and lowered for large frames (32-bit indices, ~16 GiB default workspace).  Also the
+ * most frames one lattice of tcamcrf_lattice_build can hold.  0 on invalid arguments. */
+int tcamcrf_chunk_frames(const tcamcrf_config *cfg, int N, int K, int H, int W);
 
 /* Lattice reuse.  tcamcrf_lattice_build runs the image-only stages (tables, per-pixel vertices and weights, blur
  * links: Permutohedral::init, permutohedral.cpp:115-297) for N <= chunk_frames frames into `workspace`;

@@ -90,8 +90,9 @@ class DenseCRFFilter(object):
         xy = int(self.sigma_xy * self.scale_factor)            # crf_post_processing.py:113
         cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, float(self.sigma_rgb), float(xy))
         out = torch.empty_like(unary)
-        for n0 in range(0, n, _MAX_FRAMES):
-            n1 = min(n, n0 + _MAX_FRAMES)
+        per = min(_MAX_FRAMES, ops.lattice_capacity(cfg, unary.shape[1], h, w))   # fewer for large frames
+        for n0 in range(0, n, per):
+            n1 = min(n, n0 + per)
             out[n0:n1] = self._mean_field(img[n0:n1], unary[n0:n1], cfg)
         return out.to(out_device)
 

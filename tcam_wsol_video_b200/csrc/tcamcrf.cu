@@ -229,13 +229,27 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     pl.slots = pl.geom.slots1 + pl.geom.slots2;
     float pf = cfg->pool_factor > 0.f ? cfg->pool_factor : 1.0f;
     if (pf > 1.f) pf = 1.f;
+    if (worst * pf + 64 > (double)0x7fffff00) return fail(TCAMCRF_ERR_INVALID, "image too large");
     pl.stride = ((int)(worst * pf) + 32 + 31) / 32 * 32;
+    // vertex ids, link indices ((d+1) * pool) and table entry indices (chunk * slots) are 32-bit: large frames get
+    // a smaller chunk instead of an error (the reference takes any size; frames are independent, so the chunk
+    // size never changes a result)
+    {
+        const long long lim = 0x7fffff00ll;
+        long long most = lim / ((long long)pl.stride * (D + 1));
+        if (lim / (long long)pl.slots < most) most = lim / (long long)pl.slots;
+        if (most < 1) return fail(TCAMCRF_ERR_INVALID, "image too large");
+        if (pl.chunk > most) pl.chunk = (int)most;
+    }
+    if (cfg->chunk_frames <= 0 && !getenv("TCAMCRF_CHUNK")) {
+        // default chunk: keep the workspace of large frames within ~16 GiB (64 frames of 1024x1024 would take 47)
+        const double per_frame = (double)pl.slots * sizeof(Entry) + 2.0 * (D + 1) * pl.P * 4.0 +
+                                 (double)pl.stride * (8.0 + (D + 1) * 8.0 + 2.0 * pl.Kp * 4.0);
+        long long most = (long long)(16.0 * 1024 * 1024 * 1024 / per_frame);
+        if (most < 1) most = 1;
+        if (pl.chunk > most) pl.chunk = (int)most;
+    }
     pl.pool = (long long)pl.stride * pl.chunk;
-    if (pl.pool > 0x7fffff00ll) return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
-    if ((unsigned long long)pl.slots * pl.chunk > 0x7fffff00ull)
-        return fail(TCAMCRF_ERR_INVALID, "hash tables too large; lower chunk_frames");
-    if (pl.pool * (D + 1) > 0x7fffff00ll)
-        return fail(TCAMCRF_ERR_INVALID, "vertex pool too large; lower chunk_frames");
     // + 1: the ghost pixel that stands for the reference's zero-feature padding (see build_kernel)
     pl.blocks_per_frame = (pl.P + 1 + kThreads - 1) / kThreads;
     unsigned int sig = 0x9e3779b9u;
@@ -2109,6 +2123,14 @@ static int lattice_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, v
         return fail(TCAMCRF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
     if (((uintptr_t)workspace & 255) != 0) return fail(TCAMCRF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     return TCAMCRF_OK;
+}
+
+int tcamcrf_chunk_frames(const tcamcrf_config *cfg, int N, int K, int H, int W)
+{
+    if (!cfg) return 0;
+    Plan pl;
+    if (make_plan(cfg, N, K, H, W, pl)) return 0;
+    return pl.chunk;
 }
 
 int tcamcrf_lattice_build(const tcamcrf_config *cfg, const void *images_dev, int images_u8, int N, int K, int H,

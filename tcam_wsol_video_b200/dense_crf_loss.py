@@ -44,7 +44,7 @@ class DenseCRFLossFunction(Function):
         cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
         ctx.N = n
         ctx.exact = bool(exact_gradient)
-        if ctx.exact and n <= 64:
+        if ctx.exact and n <= ops.lattice_capacity(cfg, segmentations.shape[1], *segmentations.shape[2:]):
             # keep the lattice: the backward pass runs the transposed filter on it (blur axes in reverse order)
             ctx.lattice = ops.Lattice(images, cfg, segmentations.shape[1], device=segmentations.device)
             ctx.segs = segmentations.detach()

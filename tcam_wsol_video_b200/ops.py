@@ -174,13 +174,21 @@ def crf_filter_transposed(images: torch.Tensor, segs: torch.Tensor, cfg: _lib.Co
     return out
 
 
+def lattice_capacity(cfg: _lib.Config, k: int, h: int, w: int) -> int:
+    """Most frames one lattice (one pass of the library) holds for this problem: 64 unless the frames are large."""
+    cap = _lib.load().tcamcrf_chunk_frames(byref(cfg), 1 << 20, int(k), int(h), int(w))
+    if cap <= 0:
+        raise TcamCrfError("tcamcrf_chunk_frames: " + _lib.last_error())
+    return cap
+
+
 class Lattice:
     """The permutohedral lattice of a batch of frames, built once and applied many times.
 
     Owns its workspace (the lattice lives in it).  `apply(segs)` = A segs, `apply(segs, transposed=True)` = A^T segs
     (blur axes in reverse order).  Mirrors what the reference does per image inside bilateralfilter() -- one
     Permutohedral::init, K computes (bilateralfilter.cpp:28-37) -- and backs the exact-gradient backward and the
-    mean-field iterations of DenseCRFFilter.  At most `chunk_frames` (64) frames per lattice.
+    mean-field iterations of DenseCRFFilter.  At most `lattice_capacity(...)` frames per lattice (64 unless large).
     """
 
     def __init__(self, images: torch.Tensor, cfg: _lib.Config, k: int, device: Optional[torch.device] = None):

@@ -134,6 +134,32 @@ def test_workspace_sizing_and_argument_validation():
     assert lib.tcamcrf_lattice_build(ctypes.byref(cfg), fake, 0, 2, 2, 8, 8, fake, 16, None) == 2   # workspace too small
 
 
+def test_chunk_shrinks_for_large_frames():
+    """Frames per pass: 64 by default, capped by N; large frames get a smaller chunk instead of an error (32-bit
+    vertex / entry indices, ~16 GiB default workspace) -- the reference takes any image size."""
+    lib = _lib.load()
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    chunk = lambda c, n, k, h, w: lib.tcamcrf_chunk_frames(ctypes.byref(c), n, k, h, w)
+    assert chunk(cfg, 32, 10, 224, 224) == 32
+    assert chunk(cfg, 256, 2, 224, 224) == 64
+    assert chunk(cfg, 256, 2, 448, 448) == 64
+    big = chunk(cfg, 64, 2, 1024, 1024)
+    assert 1 <= big < 64
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(cfg), 64, 2, 1024, 1024) <= 17 * 2 ** 30
+    assert chunk(cfg, 4, 2, 4096, 4096) == 1
+    # an explicit chunk is only lowered when the 32-bit indices need it
+    explicit = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, chunk_frames=64)
+    assert chunk(explicit, 64, 2, 1024, 1024) > big
+    assert chunk(explicit, 64, 2, 4096, 4096) == 3
+    assert lib.tcamcrf_workspace_bytes(ctypes.byref(explicit), 64, 2, 4096, 4096) > 0
+    # beyond any chunk size
+    assert chunk(cfg, 1, 2, 8192, 8192) == 0 and "too large" in _lib.last_error()
+    assert chunk(cfg, 0, 2, 8, 8) == 0
+    from tcam_wsol_video_b200 import ops
+    assert ops.lattice_capacity(cfg, 2, 224, 224) == 64
+    assert ops.lattice_capacity(cfg, 2, 1024, 1024) == big
+
+
 def test_dropin_modules_validate_like_the_swig_typemaps():
     from tcam_wsol_video_b200 import bilateralfilter as bf
     from tcam_wsol_video_b200 import colorbilateralfilter as cbf
