@@ -473,6 +473,34 @@ def test_row_cooperative_kernels(torch_cuda, oracle_mod, monkeypatch, kind, k, d
     assert rel_err(out["1"].cpu().numpy(), out["0"].cpu().numpy()) < 1e-5
 
 
+def test_large_frames_take_smaller_chunks(torch_cuda, oracle_mod):
+    """1024x1024 frames: the default chunk drops below 64 (tcamcrf_chunk_frames) and a batch larger than it goes
+    through several passes over one workspace; frames are independent, so the result equals the same frames
+    filtered two at a time, and frame 0 equals the oracle."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    k, h, w = 2, 1024, 1024
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    cap = ops.lattice_capacity(cfg, k, h, w)
+    assert 1 <= cap < 64
+    n = cap + 3
+    img_np = synth.make_images(n, h, w, "natural", seed=11)
+    seg_np = synth.make_segs(n, k, h, w, seed=11)
+    img = torch.from_numpy(img_np).cuda()
+    seg = torch.from_numpy(seg_np).cuda()
+    got, loss, _ = ops.crf_forward(img, seg, cfg, check=True)
+    for n0 in (0, cap - 1, n - 2):          # first chunk, across the chunk boundary, last chunk
+        part, _, _ = ops.crf_forward(img[n0:n0 + 2].contiguous(), seg[n0:n0 + 2].contiguous(), cfg, check=True)
+        assert rel_err(part.cpu().numpy(), got[n0:n0 + 2].cpu().numpy()) < 1e-5
+    want0 = oracle_mod.port_bilateralfilter_batch(img_np[:1], seg_np[:1], 1, k, h, w, 15.0, 100.0).reshape(1, k, h, w)
+    _assert_close(got[:1].cpu().numpy(), want0, "AS, 1024x1024 frame 0")
+    want_loss = -(seg.double() * got.double()).sum() / n
+    assert abs(loss.item() - want_loss.item()) < 1e-5 * abs(want_loss.item())
+    del got, img, seg, part
+    ops.release_workspaces()       # ~19 GiB: do not keep it for the rest of the session
+    torch.cuda.empty_cache()
+
+
 def test_full_size_properties_config2(torch_cuda):
     """BASELINE configs[1] at full size (32 x 10 classes x 224^2): too slow for the scalar oracle in a unit
     test, so check size-independent properties: linearity, channel independence (K=10 in one pass equals
