@@ -489,7 +489,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         # BASELINE configs[3]: lattice-size stress at 448x448 -- the 5-D colour lattice (x, y, r, g, b) and the 3-D
         # grayscale one (x, y, gray), 8 frames, K=2, noise frames (largest lattices), fwd+bwd like the headline.
         try:
-            from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLossFunction  # noqa: F401
             n4, k4, s4 = 8, 2, 448
             img4 = torch.from_numpy(synth.make_images(n4, s4, s4, "noise", seed=11)).to(dev)
             seg4 = torch.from_numpy(synth.make_segs(n4, k4, s4, s4, seed=11)).to(dev)

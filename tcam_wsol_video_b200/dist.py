@@ -15,7 +15,7 @@ One process per GPU (torchrun); ``torch.distributed`` is the plumbing.  Two conv
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
