@@ -286,6 +286,16 @@ __device__ __forceinline__ unsigned long long load_key_cg(const Entry *e)
     return __ldcg(&e->key);  // bypass L1: other SMs insert concurrently
 }
 
+// One probe: key and id of an entry with a single 16-byte load (L2; other SMs insert concurrently).  The id is
+// written by the entry's creator with a plain 4-byte store some time after its compare-and-swap, so it may still
+// read -1; it never changes once it is >= 0.
+__device__ __forceinline__ void load_entry_cg(const Entry *e, unsigned long long &key, int &id)
+{
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(e));
+    key = ((unsigned long long)v.y << 32) | v.x;
+    id = (int)v.z;
+}
+
 // Continues the insertion of `key` into the frame table `tab` (primary tier at [0, slots1), overflow at
 // [slots1, slots1+slots2)) from primary slot `h`, after `probes` primary slots have already been rejected;
 // `cur` holds the key read from slot `h`.  Callers run the first probes of all their keys in lock step

@@ -418,9 +418,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     const bool active = valid || ghost;
     const int lane = threadIdx.x & 31;
 
-    int slot[D + 1];
     unsigned long long key[D + 1];
-    float bary[D + 1];
     unsigned int wonmask = 0;
     bool ok = true;
 
@@ -441,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
             for (int c = 0; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)c * p.P), p.sigma_rgb);
         }
         int z[D + 1], rank[D + 1];
+        float bary[D + 1];
         ok = embed_point<D>(f, p.ec, z, rank, bary);
         if (!ok) {
             // keep the fields well-formed; the whole call is poisoned through the status word
@@ -451,6 +450,13 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
             }
         }
         Codec::pack_simplex(z, rank, key);
+        // The weights leave the registers here, ahead of the wait: the kernel in front of this one (prepare_kernel)
+        // is an ordinary launch, so every earlier reader of bary[] has completed before any block of this grid runs.
+        if (valid) {
+            const size_t base = (size_t)n * (D + 1) * p.P + pix;
+#pragma unroll
+            for (int r = 0; r <= D; r++) p.bary[base + (size_t)r * p.P] = bary[r];
+        }
     } else {
 #pragma unroll
         for (int r = 0; r <= D; r++) key[r] = kEmptyKey;
@@ -464,30 +470,37 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
 
     // Warp-cooperative insertion.  A warp holds 32 neighbouring pixels of one image row; in real frames
     // most of them fall on the same lattice vertices.  Lanes whose key equals their left neighbour's form a
-    // run; only the head of a run touches the table and the entry index is broadcast back to the run
+    // run; only the head of a run touches the table and the result is broadcast back to the run
     // (one SHFL + one ballot per key -- MATCH.ANY.U64 measured ~3x the short-scoreboard stalls; equal keys
     // that are not adjacent are simply inserted twice, the second insert finds the first).  A head probes
     // for all the keys it leads in lock step: every round issues one load per pending key before any result
     // is consumed, so the d+1 dependent probe chains overlap instead of running one after the other.
+    //
+    // Vertex ids at build time.  A probe is ONE 16-byte load of {key, id}: when the key is already there and its
+    // creator has published the id (blocks are interleaved across frames, so most keys are found by later waves
+    // with plain loads), the pixel gets the dense vertex id right here and the splat never has to translate the
+    // entry index -- up to 6 random look-ups and 6 stores per pixel less.  Where the id is not visible yet (-1)
+    // the entry index is kept and the splat resolves it as before.
     Entry *tab = p.table + (size_t)n * p.slots;
     const unsigned int mask1 = geom.slots1 - 1;
     unsigned int pend = 0;
-    int leader[D + 1];
-    unsigned int hh[D + 1];
+    unsigned int leaders = 0;        // 5 bits per remainder: the lane that heads this lane's run
+    int slot[D + 1];                 // the slot being probed; once the key is resolved, the slot it lives in
+    int vid[D + 1];                  // id field of the entry last probed = the vertex id once resolved (-1: unknown)
     unsigned long long cur[D + 1];
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         const unsigned long long left = __shfl_up_sync(0xffffffffu, key[r], 1);
         const bool head = lane == 0 || left != key[r];
         const unsigned int heads = __ballot_sync(0xffffffffu, head);
-        leader[r] = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // nearest head at or below this lane
-        hh[r] = 0;
-        cur[r] = 0;
+        leaders |= (unsigned int)(31 - __clz(heads & (0xffffffffu >> (31 - lane)))) << (5 * r);   // nearest head at or below
         slot[r] = -1;
+        vid[r] = -1;
+        cur[r] = 0;
         if (active && head) {
             pend |= 1u << r;
-            hh[r] = hash_primary(key[r], geom);
-            cur[r] = load_key_cg(tab + hh[r]);
+            slot[r] = (int)hash_primary(key[r], geom);
+            load_entry_cg(tab + slot[r], cur[r], vid[r]);
         }
     }
     constexpr int kLockstepRounds = 6;
@@ -498,37 +511,36 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
             if (!(pend & (1u << r))) continue;
             unsigned long long c = cur[r];
             if (c == kEmptyKey) {
-                c = atomicCAS(&tab[hh[r]].key, kEmptyKey, key[r]);
+                c = atomicCAS(&tab[slot[r]].key, kEmptyKey, key[r]);
+                vid[r] = -1;   // ours to allocate below, or created this instant by another thread
                 if (c == kEmptyKey) {
                     wonmask |= 1u << r;
                     c = key[r];
                 }
             }
-            if (c == key[r]) {
-                slot[r] = (int)hh[r];
+            if (c == key[r])
                 pend &= ~(1u << r);
-            } else {
-                hh[r] = (hh[r] + 1) & mask1;
-            }
+            else
+                slot[r] = (int)(((unsigned int)slot[r] + 1u) & mask1);
         }
 #pragma unroll
         for (int r = 0; r <= D; r++)
-            if (pend & (1u << r)) cur[r] = load_key_cg(tab + hh[r]);
+            if (pend & (1u << r)) load_entry_cg(tab + slot[r], cur[r], vid[r]);
     }
     bool table_full = false, spilled_any = false;
 #pragma unroll
     for (int r = 0; r <= D; r++) {
         if (pend & (1u << r)) {  // stragglers: long probe chains, overflow tier
             bool won, spilled;
-            slot[r] = table_insert_from(tab, geom, key[r], hh[r], (unsigned int)rounds, cur[r], won, spilled);
+            slot[r] = table_insert_from(tab, geom, key[r], (unsigned int)slot[r], (unsigned int)rounds, cur[r], won,
+                                        spilled);
+            vid[r] = -1;
             if (won) wonmask |= 1u << r;
             if (slot[r] < 0) table_full = true;
             spilled_any |= spilled;
         }
     }
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r <= D; r++) slot[r] = __shfl_sync(0xffffffffu, slot[r], leader[r]);
     if (table_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_TABLE_FULL);
     if (spilled_any) p.ctrl[kCtrlDirtyNew] = 1;
 
@@ -554,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
                 const int id = n * p.stride + local;
                 e->id = id;
                 p.vkey[id] = key[r];
+                vid[r] = id;
             } else {
                 pool_full = true;  // e->id stays -1
             }
@@ -562,13 +575,14 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     }
     if (pool_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_POOL_FULL);
 
-    if (valid) {
-        const size_t base = (size_t)n * (D + 1) * p.P + pix;
+    // what the pixel kernels find in offset[]: -2 - id (vertex id known), the entry index (>= 0: the first splat
+    // looks the id up) or -1 (no vertex: table full).  Heads hand theirs to the lanes of their run.
+    const size_t base = (size_t)n * (D + 1) * p.P + pix;
 #pragma unroll
-        for (int r = 0; r <= D; r++) {
-            p.offset[base + (size_t)r * p.P] = slot[r] < 0 ? -1 : (int)(n * p.slots + slot[r]);
-            p.bary[base + (size_t)r * p.P] = bary[r];
-        }
+    for (int r = 0; r <= D; r++) {
+        const int mine = vid[r] >= 0 ? -2 - vid[r] : (slot[r] < 0 ? -1 : (int)(n * p.slots + slot[r]));
+        const int ref = __shfl_sync(0xffffffffu, mine, (int)((leaders >> (5 * r)) & 31u));
+        if (valid) p.offset[base + (size_t)r * p.P] = ref;
     }
 }
 
