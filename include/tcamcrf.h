@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TCAMCRF_VERSION 100
+#define TCAMCRF_VERSION 101
 
 /* host-side status codes */
 #define TCAMCRF_OK 0
@@ -72,6 +72,9 @@ typedef struct tcamcrf_config {
     float pool_factor; /* vertex pool size as a fraction of the worst case (d+1)*H*W per frame; 0 -> 1.0 */
     int chunk_frames;  /* frames processed per pass (bounds the workspace); 0 -> default: 64, fewer for large frames
                           (workspace kept within ~16 GiB).  Always lowered when 32-bit vertex / entry indices need it. */
+    float loss_weight; /* the module's `weight` (dense_crf_loss.py:118-122) folded into the loss kernels:
+                          loss_dev[0] = loss_weight * (-sum(segs*AS)/n_norm), two separately rounded operations like
+                          the reference's `self.weight * Function.apply(...)`; 0 -> 1 (the plain loss) */
 } tcamcrf_config;
 
 int tcamcrf_version(void);
@@ -102,6 +105,14 @@ int tcamcrf_filter_u8(const tcamcrf_config *cfg, const uint8_t *images_dev, cons
 int tcamcrf_filter_transposed(const tcamcrf_config *cfg, const void *images_dev, int images_u8, const float *segs_dev,
                                float *ats_dev, int N, int K, int H, int W, void *workspace, size_t workspace_bytes,
                                void *cuda_stream);
+
+/* Host-side check of the packed-key range (no device work): 1 when frames whose image planes lie in
+ * [0, max_value] cannot produce a lattice coordinate outside the 64-bit packed keys for this configuration
+ * (sigma too small for the lattice dimension: the fields hold 20 bits per coordinate for d <= 3, 15 / 12 / 10 bits
+ * for d = 4 / 5 / 6), else 0.  The device detects the same condition per call (TCAMCRF_DEV_KEY_RANGE, outputs NaN);
+ * this lets a caller refuse a configuration up front with a clear message.  The reference's int16 keys wrap silently
+ * instead (permutohedral.cpp:245-248). */
+int tcamcrf_key_range_ok(const tcamcrf_config *cfg, int H, int W, float max_value);
 
 /* Frames one pass works on for this problem (what tcamcrf_workspace_bytes sizes the workspace for): cfg->chunk_frames
  * or the default 64, capped by N and lowered for large frames (32-bit indices, ~16 GiB default workspace).  Also the
@@ -151,6 +162,12 @@ int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const void *imag
 int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
                           float n_norm, void *cuda_stream);
 
+/* The same with the module's weight folded in: grad_seg = ((-2 * (grad_out[0] * weight)) * AS) / n_norm -- what
+ * autograd computes for `weight * loss` (the multiplication's backward hands grad_out * weight to
+ * DenseCRFLossFunction.backward), without the two extra elementwise launches. */
+int tcamcrf_loss_backward_weighted(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
+                                   float n_norm, float weight, void *cuda_stream);
+
 /* The same loss taken directly from LOGITS: segs = softmax(logits) over the K classes is
  * formed on the fly inside the splat and slice kernels and never stored, and the backward pass goes through the
  * softmax in the same kernel:  dz_k = p_k * (g_k - sum_j p_j g_j),  g = ((-2*grad_out)*AS)/n_norm.
@@ -161,6 +178,9 @@ int tcamcrf_loss_forward_logits(const tcamcrf_config *cfg, const void *images_de
                                 float n_norm, void *workspace, size_t workspace_bytes, void *cuda_stream);
 int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
                                  float *grad_logits_dev, int N, int K, int H, int W, float n_norm, void *cuda_stream);
+int tcamcrf_loss_backward_logits_weighted(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
+                                          float *grad_logits_dev, int N, int K, int H, int W, float n_norm,
+                                          float weight, void *cuda_stream);
 
 /* Reads the device status word of a workspace (synchronises the stream).  Returns 0 or TCAMCRF_DEV_* bits
  * in *dev_status; also writes the number of lattice vertices of the last chunk to *vertices (may be NULL). */
@@ -187,6 +207,12 @@ int colorbilateralfilter_batch(float *images, int len_images, float *ins, int le
  * images/segs in host memory, writes loss_host[0], grad_host [N,K,H,W] (for grad_out = 1 * weight). */
 int tcamcrf_loss_fwd_bwd_host(const tcamcrf_config *cfg, const float *images_host, const float *segs_host,
                               float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out);
+
+/* Tuning knobs (sweeps and tests; never needed for correctness).  The library reads TCAMCRF_<NAME> from the
+ * environment once, at first use; this sets a knob at run time instead.  name: "CHUNK", "DENSE", "HIMG_SECTIONS",
+ * "HOST_GROUPS", "HOST_SECTION0", "HOST_TRACE" (with or without the TCAMCRF_ prefix); value < 0 (or 0 where 0 is
+ * not meaningful) restores the default. */
+int tcamcrf_set_tuning(const char *name, int value);
 
 /* ---- measurement hooks (bench.py) ----
  * Stage timing brackets every pipeline stage with CUDA events on the caller's stream (not capture-safe while

@@ -152,6 +152,41 @@ def port_lattice_color(image, H, W, sigma_rgb, DIM) -> Lattice:
     return _port_lattice_from_handle(lib, h, DIM, H * W)
 
 
+def port_filter_features(features, planes) -> np.ndarray:
+    """Filters `planes` [K, n] through the lattice of explicit per-pixel features [n, d] (already divided by
+    their sigmas): Permutohedral::init + one compute per plane (permutohedral.cpp:115-297, 507-572).
+    Covers feature layouts the two reference wrappers do not build themselves (x, y, gray; d = 4)."""
+    lib = load_port()
+    features = _f32(features)
+    n, d = features.shape
+    planes = _f32(planes).reshape(-1, n)
+    h = lib.po_build(_ptr(features.ravel()), d, n)
+    if not h:
+        raise RuntimeError("po_build failed")
+    out = np.zeros_like(planes)
+    try:
+        for k in range(planes.shape[0]):
+            src = np.ascontiguousarray(planes[k])
+            dst = np.zeros(n, dtype=np.float32)
+            if lib.po_filter(h, _ptr(src), _ptr(dst)):
+                raise RuntimeError("po_filter failed")
+            out[k] = dst
+    finally:
+        lib.po_free(h)
+    return out
+
+
+def xy_features(H: int, W: int, sigma_xy: float, planes, sigma_rgb: float) -> np.ndarray:
+    """[H*W, 2 + C] features (col/sigma_xy, row/sigma_xy, plane_c/sigma_rgb ...) in float32, the arithmetic of
+    initializePermutohedral (bilateralfilter.cpp:4-19) for any number of image planes C."""
+    planes = _f32(planes).reshape(-1, H * W)
+    col = np.tile(np.arange(W, dtype=np.float32), H)
+    row = np.repeat(np.arange(H, dtype=np.float32), W)
+    feats = [col / np.float32(sigma_xy), row / np.float32(sigma_xy)]
+    feats += [planes[c] / np.float32(sigma_rgb) for c in range(planes.shape[0])]
+    return np.ascontiguousarray(np.stack(feats, axis=1).astype(np.float32))
+
+
 def port_scale_factors(d: int) -> np.ndarray:
     lib = load_port()
     sf = np.zeros(d, dtype=np.float32)

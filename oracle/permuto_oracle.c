@@ -34,11 +34,13 @@
  *     axes 0..d with a zero sentinel for missing neighbours, slice multiplies
  *     (bary*alpha) first and then the value (permutohedral.cpp:526-567).
  *
- * One deliberate difference: the reference processes pixels four at a time and
- * also inserts the zero-feature padding pixels of the last partial block
- * (permutohedral.cpp:173,238-251).  Those vertices never receive a splat, so
- * they cannot change any output; po_build reproduces them only so that the
- * vertex count M agrees with the reference when N % 4 != 0.
+ * A reference quirk reproduced on purpose: it processes pixels four at a time
+ * and also inserts the zero-feature padding pixels of the last partial block
+ * (permutohedral.cpp:173,238-251).  Those vertices never receive a splat, but
+ * they exist: they pick up values from their neighbours during the blur and
+ * hand them on, so they DO change the output (rel ~1e-2 near black pixels at
+ * the image origin) whenever N % 4 != 0.  po_build inserts them like the
+ * reference does, and M counts them.
  *
  * Parity pinned: tests/test_oracle.py checks this file bit for bit against
  * the reference's own C++ compiled unmodified into oracle/_ref/ (when

@@ -50,6 +50,7 @@ class Config(Structure):
         ("hash_load", c_float),
         ("pool_factor", c_float),
         ("chunk_frames", c_int),
+        ("loss_weight", c_float),
     ]
 
 
@@ -94,6 +95,7 @@ SIGNATURES = {
     "tcamcrf_device_count": (c_int, []),
     "tcamcrf_workspace_bytes": (c_size_t, [_cfgp, c_int, c_int, c_int, c_int]),
     "tcamcrf_chunk_frames": (c_int, [_cfgp, c_int, c_int, c_int, c_int]),
+    "tcamcrf_key_range_ok": (c_int, [_cfgp, c_int, c_int, c_float]),
     "tcamcrf_filter": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_filter_transposed": (c_int, [_cfgp, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_lattice_build": (c_int, [_cfgp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -105,6 +107,8 @@ SIGNATURES = {
     "tcamcrf_loss_forward_logits": (c_int, [_cfgp, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "tcamcrf_loss_backward_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tcamcrf_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p]),
+    "tcamcrf_loss_backward_weighted": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_void_p]),
+    "tcamcrf_loss_backward_logits_weighted": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "tcamcrf_workspace_status": (c_int, [c_void_p, c_void_p, POINTER(c_int), POINTER(c_int)]),
     "tcamcrf_debug_lattice": (c_int, [_cfgp, c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int), c_void_p, c_size_t]),
     "bilateralfilter": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float]),
@@ -112,6 +116,7 @@ SIGNATURES = {
     "colorbilateralfilter": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int]),
     "colorbilateralfilter_batch": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int]),
     "tcamcrf_loss_fwd_bwd_host": (c_int, [_cfgp, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float]),
+    "tcamcrf_set_tuning": (c_int, [c_char_p, c_int]),
     "tcamcrf_profile_enable": (None, [c_int]),
     "tcamcrf_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
     "tcamcrf_launch_count": (ctypes.c_longlong, []),
@@ -155,7 +160,35 @@ def check(rc: int, what: str) -> None:
         raise TcamCrfError(f"{what} failed (status {rc}): {last_error()}")
 
 
+def set_tuning(name: str, value: int = -1) -> None:
+    """Sets a tuning knob of the library at run time (the TCAMCRF_<NAME> environment variables are read once, at
+    first use); value < 0 restores the default.  Sweeps and tests only."""
+    check(load().tcamcrf_set_tuning(name.encode(), int(value)), "tcamcrf_set_tuning")
+
+
+_key_range_seen = {}
+
+
+def require_key_range(cfg: Config, h: int, w: int, max_value: float = 255.0) -> None:
+    """Raises a clear error when frames holding 0..max_value could leave the packed-key range of the lattice for this
+    configuration (sigma too small for the lattice dimension, or more than 6 feature dimensions) instead of letting
+    the call come back with a NaN loss.  Host arithmetic only; cached per configuration."""
+    key = (cfg.feat, cfg.channels, float(cfg.sigma_rgb), float(cfg.sigma_xy), int(h), int(w), float(max_value))
+    ok = _key_range_seen.get(key)
+    if ok is None:
+        ok = bool(load().tcamcrf_key_range_ok(ctypes.byref(cfg), int(h), int(w), float(max_value)))
+        if len(_key_range_seen) < 256:
+            _key_range_seen[key] = ok
+    if not ok:
+        d = cfg.channels + (2 if cfg.feat == FEAT_XY_RGB else 0)
+        raise TcamCrfError(
+            f"lattice configuration out of range: d={d} (supported: 1..6), sigma_rgb={cfg.sigma_rgb:g}, "
+            f"sigma_xy={cfg.sigma_xy:g}, {h}x{w} frames with values up to {max_value:g} would leave the packed "
+            f"64-bit vertex keys; use a larger sigma or fewer image planes")
+
+
 def make_config(feat: int, channels: int, sigma_rgb: float, sigma_xy: float = 1.0, image_stride_planes: int = 0,
-                hash_load: float = 0.0, pool_factor: float = 0.0, chunk_frames: int = 0) -> Config:
+                hash_load: float = 0.0, pool_factor: float = 0.0, chunk_frames: int = 0,
+                loss_weight: float = 0.0) -> Config:
     return Config(feat, channels, image_stride_planes or channels, float(sigma_rgb), float(sigma_xy),
-                  float(hash_load), float(pool_factor), int(chunk_frames))
+                  float(hash_load), float(pool_factor), int(chunk_frames), float(loss_weight))

@@ -43,6 +43,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost a pointer check when no tool is attached
 
 #include "../../include/tcamcrf.h"
 #include "lattice.cuh"
@@ -75,6 +76,38 @@ static int fail(int code, const char *fmt, ...)
             return fail(TCAMCRF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                    \
     } while (0)
+
+// ---------------------------------------------------------------------------
+// tuning knobs: read from the environment ONCE (first use), changeable at run time through
+// tcamcrf_set_tuning() -- no getenv on the call path.  0 / -1 = library default.
+// ---------------------------------------------------------------------------
+struct Tuning {
+    int chunk = 0;            // TCAMCRF_CHUNK: frames per pass (sweeps)
+    int dense = -1;           // TCAMCRF_DENSE: force the row-cooperative splat on (1) / off (0); -1 = density hint
+    int himg_sections = 0;    // TCAMCRF_HIMG_SECTIONS: sections of a chunk on the host-frames path
+    int host_groups = 0;      // TCAMCRF_HOST_GROUPS: value-stage groups per chunk on the host-pointer path
+    int host_section0 = 0;    // TCAMCRF_HOST_SECTION0: frames of the first section on the host-pointer path
+    int host_trace = 0;       // TCAMCRF_HOST_TRACE: print the timeline of host_run
+};
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static Tuning &tuning()
+{
+    static Tuning t = [] {
+        Tuning x;
+        x.chunk = env_int("TCAMCRF_CHUNK", 0);
+        x.dense = env_int("TCAMCRF_DENSE", -1);
+        x.himg_sections = env_int("TCAMCRF_HIMG_SECTIONS", 0);
+        x.host_groups = env_int("TCAMCRF_HOST_GROUPS", 0);
+        x.host_section0 = env_int("TCAMCRF_HOST_SECTION0", 0);
+        x.host_trace = getenv("TCAMCRF_HOST_TRACE") != nullptr;
+        return x;
+    }();
+    return t;
+}
 
 // ---------------------------------------------------------------------------
 // optional per-stage timing (CUDA events on the caller's stream) + launch counter
@@ -117,6 +150,10 @@ struct StageScope {
     cudaEvent_t a = nullptr;
     StageScope(int stage_, int launches_, cudaStream_t st_) : stage(stage_), launches(launches_), st(st_)
     {
+        static const char *const names[kStCount] = {"tcamcrf:build", "tcamcrf:neighbour", "tcamcrf:splat", "tcamcrf:blur",
+                                                    "tcamcrf:slice", "tcamcrf:loss", "tcamcrf:backward",
+                                                    "tcamcrf:prepare", "tcamcrf:seed"};
+        nvtxRangePushA(names[stage]);   // host-side range around the launches of the stage (nsys / ncu --nvtx)
         std::lock_guard<std::mutex> lock(g_prof.mu);
         g_prof.total_launches += launches;
         if (g_prof.enabled) {
@@ -126,6 +163,7 @@ struct StageScope {
     }
     ~StageScope()
     {
+        nvtxRangePop();
         if (!a) return;
         std::lock_guard<std::mutex> lock(g_prof.mu);
         cudaEvent_t b = g_prof.get();
@@ -166,6 +204,7 @@ struct Plan {
     long long pool;         // chunk * stride
     int blocks_per_frame;   // pixel blocks per frame
     int sig;                // plan signature stored in the workspace
+    float loss_weight;      // cfg->loss_weight (0 -> 1)
     // byte offsets into the workspace
     size_t off_ctrl, off_acc, off_partial, off_table, off_offset, off_bary, off_vkey, off_nbr, off_val0, off_val1,
         total;
@@ -201,16 +240,14 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     if (!(cfg->sigma_rgb > 0.f) || (cfg->feat == TCAMCRF_FEAT_XY_RGB && !(cfg->sigma_xy > 0.f)))
         return fail(TCAMCRF_ERR_INVALID, "sigmas must be positive");
     pl.D = D;
+    pl.loss_weight = cfg->loss_weight != 0.f ? cfg->loss_weight : 1.0f;
     pl.K = K;
     pl.Kp = K <= 2 ? K : (K + 3) / 4 * 4;  // value rows padded to whole float4s
     pl.H = H;
     pl.W = W;
     pl.P = H * W;
     int chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 64;
-    if (const char *env = getenv("TCAMCRF_CHUNK")) {   // tuning sweeps only (tools/sweep.sh)
-        const int v = atoi(env);
-        if (v > 0) chunk = v;
-    }
+    if (tuning().chunk > 0) chunk = tuning().chunk;   // tuning sweeps only (tools/sweep.sh)
     if (chunk > 256) chunk = 256;  // kMaxChunk: the vertex kernels keep a per-frame prefix sum in shared memory
     pl.chunk = chunk < N ? chunk : N;
     // every pixel (+ the ghost pixel) contributes at most d+1 distinct vertices
@@ -241,7 +278,7 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
         if (most < 1) return fail(TCAMCRF_ERR_INVALID, "image too large");
         if (pl.chunk > most) pl.chunk = (int)most;
     }
-    if (cfg->chunk_frames <= 0 && !getenv("TCAMCRF_CHUNK")) {
+    if (cfg->chunk_frames <= 0 && tuning().chunk <= 0) {
         // default chunk: keep the workspace of large frames within ~16 GiB (64 frames of 1024x1024 would take 47)
         const double per_frame = (double)pl.slots * sizeof(Entry) + 2.0 * (D + 1) * pl.P * 4.0 +
                                  (double)pl.stride * (8.0 + (D + 1) * 8.0 + 2.0 * pl.Kp * 4.0);
@@ -792,6 +829,7 @@ struct PixelParams {
     double *acc;            // running sum of seg . AS over the chunks of this call
     float *loss_out;        // non-null on the last chunk: receives -acc / n_norm
     float n_norm;
+    float loss_scale;       // the module's weight, folded in: loss = loss_scale * (-acc / n_norm)
     int P, K, Kp;
     int frame0;             // workspace frame of blockIdx.y == 0 (segs / as_out already point at that frame)
     int dense;              // host-side hint: the lattices of this workspace have been dense lately (splat variant)
@@ -1126,7 +1164,10 @@ __device__ __forceinline__ void fold_loss_partials(const PixelParams &p)
         if (p.loss_out) {
             // loss = -(sum)/n_norm, NaN when the device status is set (dense_crf_loss.py:63-64)
             const float s = (float)total;
-            p.loss_out[0] = p.ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(-s, p.n_norm);
+            // weight * loss as two separately rounded operations, like `self.weight * Function.apply(...)`
+            // (dense_crf_loss.py:118-122); loss_scale = 1 leaves the bits of the plain loss untouched
+            p.loss_out[0] = p.ctrl[kCtrlStatus] != 0 ? __int_as_float(0x7fc00000)
+                                                     : __fmul_rn(p.loss_scale, __fdiv_rn(-s, p.n_norm));
         }
     }
 }
@@ -1204,9 +1245,11 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
 // grad = ((-2*g) * AS) / n  with the reference's rounding order (dense_crf_loss.py:73)
 __global__ void __launch_bounds__(kThreads) loss_backward_kernel(const float *__restrict__ as,
                                                                  const float *__restrict__ grad_out,
-                                                                 float *__restrict__ grad, size_t count, float n_norm)
+                                                                 float *__restrict__ grad, size_t count, float n_norm,
+                                                                 float weight)
 {
-    const float t = __fmul_rn(-2.0f, __ldg(grad_out));
+    // grad_out * weight first: what autograd hands DenseCRFLossFunction.backward for `weight * loss`
+    const float t = __fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight));
     // vector path only when both buffers are 16-byte aligned (sub-batches of odd-sized frames are not)
     const bool aligned = ((reinterpret_cast<uintptr_t>(as) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
     const size_t n4 = aligned ? count / 4 : 0;
@@ -1233,9 +1276,9 @@ __global__ void __launch_bounds__(kThreads) loss_backward_logits_kernel(const fl
                                                                         const float *__restrict__ logits,
                                                                         const float *__restrict__ grad_out,
                                                                         float *__restrict__ grad, int K, int P,
-                                                                        long long pixels, float n_norm)
+                                                                        long long pixels, float n_norm, float weight)
 {
-    const float t = __fmul_rn(-2.0f, __ldg(grad_out));
+    const float t = __fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight));
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < pixels; i += stride) {
         const long long n = i / P;
@@ -1503,7 +1546,6 @@ struct DensityHints {
     std::vector<Slot> slots;   // a handful of workspaces per process
     cudaStream_t side = nullptr;                   // the copies run here, off the caller's stream
     cudaEvent_t ev = nullptr;
-    int device = -1;
     // caller holds `mu`
     Slot *find(void *ws, bool create)
     {
@@ -1520,7 +1562,20 @@ struct DensityHints {
         return &slots.back();
     }
 };
-static DensityHints g_hints;
+// Process-level helpers (density hints, the copy lane of the host-frames path, the host-pointer context) exist once
+// PER DEVICE: a process that drives several GPUs (threads of DataParallel, or alternating cuda:0 / cuda:1) gets
+// separate streams, events and buffers for each, and nothing is re-created or leaked on a device switch.
+constexpr int kMaxDevices = 64;
+static int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+static DensityHints g_hints_dev[kMaxDevices];
 
 static bool stream_is_capturing(cudaStream_t st)
 {
@@ -1536,6 +1591,7 @@ static bool stream_is_capturing(cudaStream_t st)
 static int density_hint(void *ws)
 {
     if (!TCAMCRF_DENSITY_HINT) return 0;
+    DensityHints &g_hints = g_hints_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_hints.mu);
     DensityHints::Slot *slot = g_hints.find(ws, false);
     return slot ? *(volatile int *)slot->word : 0;
@@ -1547,6 +1603,7 @@ static int density_hint(void *ws)
 static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
 {
     if (!TCAMCRF_DENSITY_HINT) return;
+    DensityHints &g_hints = g_hints_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_hints.mu);
     DensityHints::Slot *slot = g_hints.find(ws, true);
     if (!slot) return;
@@ -1555,16 +1612,13 @@ static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
     const unsigned int c = slot->calls++;
     if (c >= 2 && (c & 7u) != 0) return;
     if (stream_is_capturing(st)) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
-    if (g_hints.device != dev || !g_hints.side) {   // one process drives one GPU; re-create if that ever changes
+    if (!g_hints.side) {   // this device's side stream, created on first use
         if (cudaStreamCreateWithFlags(&g_hints.side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&g_hints.ev, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             g_hints.side = nullptr;
             return;
         }
-        g_hints.device = dev;
     }
     cudaEventRecord(g_hints.ev, st);
     cudaStreamWaitEvent(g_hints.side, g_hints.ev, 0);
@@ -1611,13 +1665,14 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
     pp.acc = (double *)(ws + pl.off_acc);
     pp.loss_out = loss_final;
     pp.n_norm = n_norm;
+    pp.loss_scale = pl.loss_weight;
     pp.P = pl.P;
     pp.K = pl.K;
     pp.Kp = pl.Kp;
     pp.frame0 = frame0;
     // dense lattice lately (more than one vertex per four pixels in the fullest frame): row-cooperative splat
     pp.dense = (long long)density_hint(ws) * 4 > (long long)pl.P ? 1 : 0;
-    if (const char *env = getenv("TCAMCRF_DENSE")) pp.dense = atoi(env) != 0;   // tests and sweeps: force either way
+    if (tuning().dense >= 0) pp.dense = tuning().dense != 0;   // tests and sweeps: force either way
     pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
     {
@@ -1698,21 +1753,13 @@ static int run_chunk(const tcamcrf_config *cfg, const Plan &pl, bool u8, const v
 // captured in a CUDA graph (pinned source).
 struct CopyLane {
     std::mutex mu;
-    int device = -1;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;
     size_t next = 0;
-    int ready()
+    int ready()   // this device's copy stream, created on first use
     {
-        int dev = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        if (device == dev && stream) return TCAMCRF_OK;
-        // one process drives one GPU; re-created if that ever changes (the old objects are leaked on purpose:
-        // work may still be queued on them)
+        if (stream) return TCAMCRF_OK;
         CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        events.clear();
-        next = 0;
-        device = dev;
         return TCAMCRF_OK;
     }
     int event(cudaEvent_t *ev)
@@ -1728,7 +1775,7 @@ struct CopyLane {
         return TCAMCRF_OK;
     }
 };
-static CopyLane g_lane;
+static CopyLane g_lane_dev[kMaxDevices];
 
 // One chunk whose frames come from the host: `img_host` / `img_dev` point at frame 0 of the chunk.
 static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, bool u8, const char *img_host,
@@ -1738,14 +1785,12 @@ static int run_chunk_host_frames(const tcamcrf_config *cfg, const Plan &pl, bool
 {
     // sections of at least 4 frames, 4 per chunk by default (32 frames: 8 + 8 + 8 + 8)
     int nsec = 4;
-    if (const char *env = getenv("TCAMCRF_HIMG_SECTIONS")) {
-        const int v = atoi(env);
-        if (v >= 1 && v <= 64) nsec = v;
-    }
+    if (tuning().himg_sections >= 1 && tuning().himg_sections <= 64) nsec = tuning().himg_sections;
     int per = (nc + nsec - 1) / nsec;
     if (per < 4) per = nc < 4 ? nc : 4;
     const size_t elem = u8 ? 1 : sizeof(float);
     const size_t frame = (size_t)cfg->image_stride_planes * pl.P;   // elements per image
+    CopyLane &g_lane = g_lane_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_lane.mu);
     int rc = g_lane.ready();
     if (rc) return rc;
@@ -1819,7 +1864,6 @@ static int run_filter(const tcamcrf_config *cfg, bool u8, const void *images, co
 // ---------------------------------------------------------------------------
 struct HostCtx {
     std::mutex mu;
-    int device = -1;
     void *buf = nullptr;
     size_t cap = 0;
     cudaStream_t stream = nullptr;   // compute
@@ -1827,24 +1871,10 @@ struct HostCtx {
     cudaStream_t s_out = nullptr;    // device -> host copies
     std::vector<cudaEvent_t> events;
 };
-static HostCtx g_host;
+static HostCtx g_host_dev[kMaxDevices];
 
-static int host_reserve(size_t bytes, char **out)
+static int host_reserve(HostCtx &g_host, size_t bytes, char **out)
 {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (g_host.device != dev) {
-        for (cudaStream_t *s : {&g_host.stream, &g_host.s_in, &g_host.s_out}) {
-            if (*s) cudaStreamDestroy(*s);
-            *s = nullptr;
-        }
-        for (cudaEvent_t e : g_host.events) cudaEventDestroy(e);
-        g_host.events.clear();
-        if (g_host.buf) cudaFree(g_host.buf);
-        g_host.buf = nullptr;
-        g_host.cap = 0;
-        g_host.device = dev;
-    }
     for (cudaStream_t *s : {&g_host.stream, &g_host.s_in, &g_host.s_out})
         if (!*s) CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     if (g_host.cap < bytes) {
@@ -1858,7 +1888,7 @@ static int host_reserve(size_t bytes, char **out)
     return TCAMCRF_OK;
 }
 
-static int host_event(size_t i, cudaEvent_t *ev)
+static int host_event(HostCtx &g_host, size_t i, cudaEvent_t *ev)
 {
     while (g_host.events.size() <= i) {
         cudaEvent_t e = nullptr;
@@ -1877,7 +1907,7 @@ struct HostTrace {
     cudaEvent_t t0 = nullptr;
     void begin(cudaStream_t s)
     {
-        on = getenv("TCAMCRF_HOST_TRACE") != nullptr;
+        on = tuning().host_trace != 0;
         if (!on) return;
         cudaEventCreate(&t0);
         cudaEventRecord(t0, s);
@@ -1933,13 +1963,11 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     if (rc) return rc;
     // groups of frames per chunk for the value stages (measured on B200, tools/e2e_sweep.sh)
     int want_groups = K >= 6 ? 8 : 2;
-    if (const char *env = getenv("TCAMCRF_HOST_GROUPS")) {
-        const int v = atoi(env);
-        if (v >= 1 && v <= 64) want_groups = v;
-    }
+    if (tuning().host_groups >= 1 && tuning().host_groups <= 64) want_groups = tuning().host_groups;
     int group = (pl.chunk + want_groups - 1) / want_groups;
     if (group < 1) group = 1;
     const int ngroups = N;   // upper bound: a group holds at least one frame
+    HostCtx &g_host = g_host_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_host.mu);
     const size_t P = (size_t)H * W;
     const size_t img_frame = (size_t)cfg.image_stride_planes * P;   // floats per image
@@ -1948,7 +1976,7 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     const size_t seg_bytes = align_up((size_t)N * seg_frame * sizeof(float), 256);
     const size_t scal_bytes = align_up((size_t)(2 * ngroups + 2) * sizeof(float), 256);
     char *base = nullptr;
-    rc = host_reserve(img_bytes + 3 * seg_bytes + scal_bytes + pl.total, &base);
+    rc = host_reserve(g_host, img_bytes + 3 * seg_bytes + scal_bytes + pl.total, &base);
     if (rc) return rc;
     float *d_img = (float *)base;
     float *d_seg = (float *)(base + img_bytes);
@@ -1975,14 +2003,11 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
         // Measured on B200, 32 frames (frames/s): K=10: one section 14.6 k, first section 4 frames 15.1 k;
         // K=2: one section 28.2 k, first section 16 frames 32.5 k.
         int sec0 = cn >= 16 ? (K >= 6 ? (cn + 7) / 8 : (cn + 1) / 2) : cn;
-        if (const char *env = getenv("TCAMCRF_HOST_SECTION0")) {
-            const int v = atoi(env);
-            if (v >= 1) sec0 = v < cn ? v : cn;
-        }
+        if (tuning().host_section0 >= 1) sec0 = tuning().host_section0 < cn ? tuning().host_section0 : cn;
         for (int f0 = 0, fn = 0; f0 < cn; f0 += fn) {
             fn = f0 == 0 ? sec0 : cn - f0;
             cudaEvent_t ev_img;
-            rc = host_event(ev_i++, &ev_img);
+            rc = host_event(g_host, ev_i++, &ev_img);
             if (rc) return rc;
             // only the planes the kernels read: the very last image may be shorter than the stride
             // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
@@ -2001,9 +2026,9 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
                 const int left = f0 + fn - g0;
                 nc = left < group ? left : group;
                 cudaEvent_t ev_in, ev_done;
-                rc = host_event(ev_i++, &ev_in);
+                rc = host_event(g_host, ev_i++, &ev_in);
                 if (rc) return rc;
-                rc = host_event(ev_i++, &ev_done);
+                rc = host_event(g_host, ev_i++, &ev_done);
                 if (rc) return rc;
                 CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame,
                                          (size_t)nc * seg_frame * sizeof(float), cudaMemcpyHostToDevice, s_in));
@@ -2023,7 +2048,8 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
                     if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
                     if (blocks < 1) blocks = 1;
                     loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
-                                                                                d_grad + n0 * seg_frame, count, (float)N);
+                                                                                d_grad + n0 * seg_frame, count, (float)N,
+                                                                                1.0f);
                 }
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaEventRecord(ev_done, st));
@@ -2071,7 +2097,27 @@ static tcamcrf_config ref_config(int feat, int channels, int stride, float srgb,
     c.image_stride_planes = stride;
     c.sigma_rgb = srgb;
     c.sigma_xy = sxy;
+    c.loss_weight = 0.f;
     return c;
+}
+
+// |lattice coordinate quotient| a frame can reach when every image plane lies in [0, max_value] (features are
+// non-negative): el[0] = sum_i cf_i and el[j] = sum_{i >= j} cf_i - j * cf_{j-1} with cf_i = f_i * scale_i
+// (embed_point), so |el| <= max(sum_i cf_i, max_j j * cf_{j-1}); the quotient is el / (d+1) rounded, moved by at
+// most one by the rank fix-up, and needs room for one neighbour step on either side.
+template <int D>
+static bool key_range_ok(const float (&fmax)[kMaxD])
+{
+    EmbedConsts ec;
+    scale_factors(D, ec);
+    double sum = 0.0, worst = 0.0;
+    for (int i = 0; i < D; i++) {
+        const double cf = (double)fmax[i] * (double)ec.scale[i];
+        sum += cf;
+        if ((i + 1) * cf > worst) worst = (i + 1) * cf;
+    }
+    if (sum > worst) worst = sum;
+    return worst / (D + 1) + 3.0 <= (double)KeyCodec<D>::kQMax;
 }
 
 }  // namespace tcamcrf
@@ -2137,6 +2183,30 @@ static int lattice_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, v
         return fail(TCAMCRF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total);
     if (((uintptr_t)workspace & 255) != 0) return fail(TCAMCRF_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     return TCAMCRF_OK;
+}
+
+int tcamcrf_key_range_ok(const tcamcrf_config *cfg, int H, int W, float max_value)
+{
+    const int D = feature_dim(cfg);
+    if (D < 1 || D > kMaxD || H < 1 || W < 1 || !(cfg->sigma_rgb > 0.f)) return 0;
+    float fmax[kMaxD] = {0};
+    int c0 = 0;
+    if (cfg->feat == TCAMCRF_FEAT_XY_RGB) {
+        if (!(cfg->sigma_xy > 0.f)) return 0;
+        fmax[0] = (float)(W - 1) / cfg->sigma_xy;
+        if (D > 1) fmax[1] = (float)(H - 1) / cfg->sigma_xy;
+        c0 = 2;
+    }
+    for (int c = c0; c < D; c++) fmax[c] = max_value / cfg->sigma_rgb;
+    switch (D) {
+    case 1: return key_range_ok<1>(fmax);
+    case 2: return key_range_ok<2>(fmax);
+    case 3: return key_range_ok<3>(fmax);
+    case 4: return key_range_ok<4>(fmax);
+    case 5: return key_range_ok<5>(fmax);
+    case 6: return key_range_ok<6>(fmax);
+    }
+    return 0;
 }
 
 int tcamcrf_chunk_frames(const tcamcrf_config *cfg, int N, int K, int H, int W)
@@ -2226,6 +2296,14 @@ int tcamcrf_loss_forward_logits(const tcamcrf_config *cfg, const void *images_de
 int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
                                  float *grad_logits_dev, int N, int K, int H, int W, float n_norm, void *cuda_stream)
 {
+    return tcamcrf_loss_backward_logits_weighted(as_dev, logits_dev, grad_out_dev, grad_logits_dev, N, K, H, W, n_norm,
+                                                 1.0f, cuda_stream);
+}
+
+int tcamcrf_loss_backward_logits_weighted(const float *as_dev, const float *logits_dev, const float *grad_out_dev,
+                                          float *grad_logits_dev, int N, int K, int H, int W, float n_norm,
+                                          float weight, void *cuda_stream)
+{
     if (!as_dev || !logits_dev || !grad_out_dev || !grad_logits_dev)
         return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     if (N < 1 || K < 2 || H < 1 || W < 1) return fail(TCAMCRF_ERR_INVALID, "N,H,W must be positive and K >= 2");
@@ -2235,13 +2313,19 @@ int tcamcrf_loss_backward_logits(const float *as_dev, const float *logits_dev, c
     if (blocks > cap) blocks = cap;
     StageScope scope(kStBackward, 1, (cudaStream_t)cuda_stream);
     loss_backward_logits_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)cuda_stream>>>(
-        as_dev, logits_dev, grad_out_dev, grad_logits_dev, K, H * W, pixels, n_norm);
+        as_dev, logits_dev, grad_out_dev, grad_logits_dev, K, H * W, pixels, n_norm, weight);
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;
 }
 
 int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
                           float n_norm, void *cuda_stream)
+{
+    return tcamcrf_loss_backward_weighted(as_dev, grad_out_dev, grad_seg_dev, count, n_norm, 1.0f, cuda_stream);
+}
+
+int tcamcrf_loss_backward_weighted(const float *as_dev, const float *grad_out_dev, float *grad_seg_dev, size_t count,
+                                   float n_norm, float weight, void *cuda_stream)
 {
     if (!as_dev || !grad_out_dev || !grad_seg_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     if (count == 0) return TCAMCRF_OK;
@@ -2253,7 +2337,8 @@ int tcamcrf_loss_backward(const float *as_dev, const float *grad_out_dev, float 
     if (blocks < 1) blocks = 1;
     StageScope scope(kStBackward, 1, (cudaStream_t)cuda_stream);
     loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)cuda_stream>>>(as_dev, grad_out_dev,
-                                                                                       grad_seg_dev, count, n_norm);
+                                                                                       grad_seg_dev, count, n_norm,
+                                                                                       weight);
     CUDA_TRY(cudaGetLastError());
     return TCAMCRF_OK;
 }
@@ -2283,11 +2368,12 @@ int tcamcrf_debug_lattice(const tcamcrf_config *cfg, const float *image_host, in
     if (rc) return rc;
     const size_t P = (size_t)H * W;
     const int dp1 = pl.D + 1;
+    HostCtx &g_host = g_host_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_host.mu);
     const size_t img_bytes = align_up((size_t)c.channels * P * sizeof(float), 256);
     const size_t seg_bytes = align_up(P * sizeof(float), 256);
     char *base = nullptr;
-    rc = host_reserve(img_bytes + 2 * seg_bytes + pl.total, &base);
+    rc = host_reserve(g_host, img_bytes + 2 * seg_bytes + pl.total, &base);
     if (rc) return rc;
     float *d_img = (float *)base, *d_seg = (float *)(base + img_bytes), *d_as = (float *)(base + img_bytes + seg_bytes);
     char *d_ws = base + img_bytes + 2 * seg_bytes;
@@ -2385,6 +2471,21 @@ int tcamcrf_loss_fwd_bwd_host(const tcamcrf_config *cfg, const float *images_hos
 {
     if (!loss_host || !grad_host) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
     return host_run(cfg, images_host, segs_host, nullptr, loss_host, grad_host, N, K, H, W, grad_out);
+}
+
+int tcamcrf_set_tuning(const char *name, int value)
+{
+    if (!name) return fail(TCAMCRF_ERR_INVALID, "null knob name");
+    if (strncmp(name, "TCAMCRF_", 8) == 0) name += 8;
+    Tuning &t = tuning();
+    if (!strcmp(name, "CHUNK")) t.chunk = value > 0 ? value : 0;
+    else if (!strcmp(name, "DENSE")) t.dense = value < 0 ? -1 : (value != 0);
+    else if (!strcmp(name, "HIMG_SECTIONS")) t.himg_sections = value > 0 ? value : 0;
+    else if (!strcmp(name, "HOST_GROUPS")) t.host_groups = value > 0 ? value : 0;
+    else if (!strcmp(name, "HOST_SECTION0")) t.host_section0 = value > 0 ? value : 0;
+    else if (!strcmp(name, "HOST_TRACE")) t.host_trace = value > 0;
+    else return fail(TCAMCRF_ERR_INVALID, "unknown tuning knob '%s'", name);
+    return TCAMCRF_OK;
 }
 
 void tcamcrf_profile_enable(int on)

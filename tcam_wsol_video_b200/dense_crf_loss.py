@@ -35,14 +35,28 @@ def _scale_segs(segmentations: torch.Tensor, scale_factor: float) -> torch.Tenso
                          recompute_scale_factor=False, align_corners=False)
 
 
+def _folded_weight(weight):
+    """The module's weight as a python float when it can be folded into the loss kernels (cfg.loss_weight and the
+    weighted backward: same two roundings as ``weight * loss`` and its autograd backward, three launches less per
+    step), else None (tensor weights, zero): the caller then multiplies like the reference does."""
+    if isinstance(weight, bool) or not isinstance(weight, (int, float)):
+        return None
+    w = float(weight)
+    if w == 0.0 or w != w or w in (float('inf'), float('-inf')):
+        return None
+    return w
+
+
 class DenseCRFLossFunction(Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type='cuda')
-    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False):
+    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False, weight=1.0):
         n = segmentations.shape[0]
-        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
+        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy, loss_weight=weight)
+        _lib.require_key_range(cfg, segmentations.shape[2], segmentations.shape[3])
         ctx.N = n
+        ctx.weight = float(weight)
         ctx.exact = bool(exact_gradient)
         if ctx.exact and n <= ops.lattice_capacity(cfg, segmentations.shape[1], *segmentations.shape[2:]):
             # keep the lattice: the backward pass runs the transposed filter on it (blur axes in reverse order)
@@ -71,10 +85,10 @@ class DenseCRFLossFunction(Function):
             else:
                 cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, ctx.sigmas[0], ctx.sigmas[1])
                 ats = ops.crf_filter_transposed(ctx.images, ctx.segs, cfg)
-            grad_segmentation = ops.crf_backward((ctx.AS + ats) * 0.5, grad_output, float(ctx.N))
+            grad_segmentation = ops.crf_backward((ctx.AS + ats) * 0.5, grad_output, float(ctx.N), ctx.weight)
         else:
-            grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N))
-        return None, grad_segmentation, None, None, None
+            grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N), ctx.weight)
+        return None, grad_segmentation, None, None, None, None
 
 
 class DenseCRFLoss(nn.Module):
@@ -102,6 +116,10 @@ class DenseCRFLoss(nn.Module):
         """
         scaled_images = _scale_images(images, self.scale_factor)
         scaled_segs = _scale_segs(segmentations, self.scale_factor)
+        w = _folded_weight(self.weight)
+        if w is not None:   # weight * loss formed inside the loss kernels (same roundings, no extra launches)
+            return DenseCRFLossFunction.apply(
+                scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient, w)
         val = self.weight * DenseCRFLossFunction.apply(
             scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient)
         return val
@@ -118,20 +136,23 @@ class DenseCRFLossFromLogitsFunction(Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, images, logits, sigma_rgb, sigma_xy):
+    def forward(ctx, images, logits, sigma_rgb, sigma_xy, weight=1.0):
         n = logits.shape[0]
-        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy)
+        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy, loss_weight=weight)
+        _lib.require_key_range(cfg, logits.shape[2], logits.shape[3])
         logits = logits.detach().contiguous()
         as_t, loss, _ = ops.crf_forward_logits(images, logits, cfg, n_norm=float(n))
         ctx.AS = as_t
         ctx.logits = logits
         ctx.N = n
+        ctx.weight = float(weight)
         return loss
 
     @staticmethod
     @torch.amp.custom_bwd(device_type='cuda')
     def backward(ctx, grad_output):
-        return None, ops.crf_backward_logits(ctx.AS, ctx.logits, grad_output, float(ctx.N)), None, None
+        return (None, ops.crf_backward_logits(ctx.AS, ctx.logits, grad_output, float(ctx.N), ctx.weight), None, None,
+                None)
 
 
 class DenseCRFLossFromLogits(nn.Module):
@@ -149,6 +170,9 @@ class DenseCRFLossFromLogits(nn.Module):
         self.scale_factor = scale_factor
 
     def forward(self, images, logits):
+        w = _folded_weight(self.weight)
+        if w is not None:
+            return DenseCRFLossFromLogitsFunction.apply(images, logits, self.sigma_rgb, self.sigma_xy, w)
         return self.weight * DenseCRFLossFromLogitsFunction.apply(images, logits, self.sigma_rgb, self.sigma_xy)
 
     def extra_repr(self):

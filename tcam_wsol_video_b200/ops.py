@@ -51,8 +51,30 @@ def _prep_images(images: torch.Tensor, device: torch.device) -> Tuple[torch.Tens
         if images.dtype != torch.float32:
             images = images.float()
     if images.device != device:
+        if images.device.type == 'cpu' and not images.is_pinned():
+            _warn_pageable_once(images)
         images = images.to(device, non_blocking=True)
     return images.contiguous(), u8
+
+
+_warned_pageable = False
+
+
+def _warn_pageable_once(images: torch.Tensor) -> None:
+    """Pageable host frames work (it is what the reference's trainer passes, train_wsol.py:1128) but the copy is
+    staged by the driver and blocks the host; pinned uint8 frames take the overlapped path at a quarter of the
+    bytes.  Said once per process."""
+    global _warned_pageable
+    if _warned_pageable:
+        return
+    _warned_pageable = True
+    import warnings
+    warnings.warn(
+        "tcam_wsol_video_b200: images arrive in pageable host memory (%s, %.1f MB per call): the copy blocks the "
+        "host and cannot overlap the lattice build.  Pin the loader's frames (DataLoader(pin_memory=True)) and keep "
+        "them uint8 to take the overlapped path (tcamcrf_loss_forward_host_frames)."
+        % (str(images.dtype).replace('torch.', ''), images.numel() * images.element_size() / 1e6),
+        RuntimeWarning, stacklevel=4)
 
 
 def _host_frames(images: torch.Tensor, device: torch.device) -> bool:
@@ -203,7 +225,7 @@ class Lattice:
         if c < cfg.channels:
             raise TcamCrfError(f"images have {c} planes, config needs {cfg.channels}")
         self.cfg = _lib.Config(cfg.feat, cfg.channels, c, cfg.sigma_rgb, cfg.sigma_xy, cfg.hash_load,
-                               cfg.pool_factor, cfg.chunk_frames)
+                               cfg.pool_factor, cfg.chunk_frames, cfg.loss_weight)
         self.shape = (n, int(k), h, w)
         self.device = device
         with torch.cuda.device(device):
@@ -297,8 +319,10 @@ def crf_forward_logits(images: torch.Tensor, logits: torch.Tensor, cfg: _lib.Con
     return as_out, loss, ws
 
 
-def crf_backward_logits(as_t: torch.Tensor, logits: torch.Tensor, grad_output: torch.Tensor, n_norm: float):
-    """Gradient w.r.t. the logits (CRF gradient chained through the softmax) in one kernel."""
+def crf_backward_logits(as_t: torch.Tensor, logits: torch.Tensor, grad_output: torch.Tensor, n_norm: float,
+                        weight: float = 1.0):
+    """Gradient w.r.t. the logits (CRF gradient chained through the softmax) in one kernel; `weight`: the module's
+    weight when it was folded into the forward (cfg.loss_weight)."""
     lib = _lib.load()
     _require_cuda(as_t, "AS")
     n, k, h, w = as_t.shape
@@ -306,21 +330,24 @@ def crf_backward_logits(as_t: torch.Tensor, logits: torch.Tensor, grad_output: t
     g = grad_output.detach().reshape(-1)[:1].to(device=as_t.device, dtype=torch.float32).contiguous()
     grad = torch.empty_like(as_t)
     with torch.cuda.device(as_t.device):
-        _lib.check(lib.tcamcrf_loss_backward_logits(as_t.data_ptr(), logits.data_ptr(), g.data_ptr(), grad.data_ptr(),
-                                                    n, k, h, w, float(n_norm), _stream_ptr(as_t.device)),
-                   "tcamcrf_loss_backward_logits")
+        _lib.check(lib.tcamcrf_loss_backward_logits_weighted(as_t.data_ptr(), logits.data_ptr(), g.data_ptr(),
+                                                             grad.data_ptr(), n, k, h, w, float(n_norm), float(weight),
+                                                             _stream_ptr(as_t.device)),
+                   "tcamcrf_loss_backward_logits_weighted")
     return grad
 
 
-def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float) -> torch.Tensor:
-    """grad_seg = ((-2*g) * AS) / n_norm on the current stream (dlib/crf/dense_crf_loss.py:73)."""
+def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float, weight: float = 1.0) -> torch.Tensor:
+    """grad_seg = ((-2*(g*weight)) * AS) / n_norm on the current stream (dlib/crf/dense_crf_loss.py:73; `weight`: the
+    module's weight when it was folded into the forward, cfg.loss_weight)."""
     lib = _lib.load()
     _require_cuda(as_t, "AS")
     g = grad_output.detach().reshape(-1)[:1].to(device=as_t.device, dtype=torch.float32).contiguous()
     grad = torch.empty_like(as_t)
     with torch.cuda.device(as_t.device):
-        _lib.check(lib.tcamcrf_loss_backward(as_t.data_ptr(), g.data_ptr(), grad.data_ptr(), as_t.numel(),
-                                             float(n_norm), _stream_ptr(as_t.device)), "tcamcrf_loss_backward")
+        _lib.check(lib.tcamcrf_loss_backward_weighted(as_t.data_ptr(), g.data_ptr(), grad.data_ptr(), as_t.numel(),
+                                                      float(n_norm), float(weight), _stream_ptr(as_t.device)),
+                   "tcamcrf_loss_backward_weighted")
     return grad
 
 

@@ -15,7 +15,8 @@ reference's.  ``rng_parity=False`` draws everything in one call (same distributi
 
 ``use_roi=True`` with ``roi=None``: the reference computes the ROI on the CPU with scikit-image's Otsu, one
 sample at a time (tcam_seeding.py:476-479); here ``roi_method='roi_all'`` runs as one kernel for the batch
-(``tcam_otsu_roi``).  The connected-component ROI modes still raise.
+(``tcam_otsu_roi``) and the two connected-component modes (``roi_high_density``, ``largest``)
+as one kernel too (``tcam_roi_components``).
 """
 from __future__ import annotations
 

@@ -53,8 +53,16 @@ def _worker(rank, world, port, n_total, out_dir):
         loss.backward()
         loss2 = mod(images[lo:hi], local_segs.detach(), global_batch=n_total)
         local_only = ShardedCRFLoss(StandInCRF(weight=1e-3), reduction="local")(images[lo:hi], local_segs.detach())
+        # "global_async": the forward returns this rank's share (same gradient), the reduced value arrives later
+        seg_async = segs[lo:hi].clone().requires_grad_(True)
+        mod_async = ShardedCRFLoss(StandInCRF(weight=1e-3), reduction="global_async")
+        assert mod_async.global_loss() is None
+        share = mod_async(images[lo:hi], seg_async, global_batch=n_total)
+        share.backward()
+        async_total = mod_async.global_loss().clone()
         torch.save({"loss": loss.detach(), "loss2": loss2.detach(), "grad": local_segs.grad, "lo": lo, "hi": hi,
-                    "local": local_only.detach()}, os.path.join(out_dir, f"rank{rank}.pt"))
+                    "local": local_only.detach(), "share": share.detach(), "async_total": async_total,
+                    "async_grad": seg_async.grad}, os.path.join(out_dir, f"rank{rank}.pt"))
         # all_reduce_scalar is the identity in the backward pass
         v = torch.tensor([float(rank + 1)], requires_grad=True)
         s = all_reduce_scalar(v * 2.0)
@@ -80,7 +88,12 @@ def test_sharded_loss_matches_single_process(tmp_path, n_total):
         assert torch.allclose(d["loss2"], ref.detach(), rtol=1e-6)
         assert torch.allclose(d["grad"], segs.grad[d["lo"]:d["hi"]], rtol=1e-5, atol=1e-12)
         covered += list(range(d["lo"], d["hi"]))
+        # the asynchronous reduction: same reduced value, same gradient, and the shares add up to the loss
+        assert torch.allclose(d["async_total"], ref.detach(), rtol=1e-6)
+        assert torch.equal(d["async_grad"], d["grad"])
     assert covered == list(range(n_total))
+    shares = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))["share"] for r in range(world)]
+    assert torch.allclose(sum(shares), ref.detach(), rtol=1e-6)
     # "local" reduction is the reference's DDP convention: mean of the local means == global mean only for equal shards
     if n_total % world == 0:
         locs = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))["local"] for r in range(world)]

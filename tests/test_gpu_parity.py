@@ -29,6 +29,20 @@ def torch_cuda():
     return torch
 
 
+@pytest.fixture
+def tuning():
+    """Sets library tuning knobs for one test (tcamcrf_set_tuning) and restores the defaults afterwards."""
+    touched = []
+
+    def set_(name, value):
+        touched.append(name)
+        _lib.set_tuning(name, -1 if value is None else int(value))
+
+    yield set_
+    for name in touched:
+        _lib.set_tuning(name, -1)
+
+
 def _gpu_filter_host(img, seg, srgb, sxy, dim=0):
     """AS through the drop-in host API (reference names, numpy 1-D contract)."""
     from tcam_wsol_video_b200 import bilateralfilter as bf
@@ -219,16 +233,13 @@ def test_single_image_entry_points(torch_cuda, oracle_mod):
 
 
 @pytest.mark.parametrize("n,groups", [(70, None), (7, "3"), (5, "16"), (33, "1")])
-def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, monkeypatch, n, groups):
+def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, tuning, n, groups):
     """Host-pointer path: the lattice of a whole chunk (<= 64 frames) is built at once, the value stages run group
     by group with a frame offset; more than 64 frames take several chunks.  Ragged group / chunk sizes included.
     Also the fused loss + gradient entry point (tcamcrf_loss_fwd_bwd_host)."""
     import ctypes
     from tcam_wsol_video_b200 import _lib
-    if groups is None:
-        monkeypatch.delenv("TCAMCRF_HOST_GROUPS", raising=False)
-    else:
-        monkeypatch.setenv("TCAMCRF_HOST_GROUPS", groups)
+    tuning("HOST_GROUPS", groups)
     k, h, w = 3, 13, 18
     img = synth.make_images(n, h, w, "noise", seed=n)
     seg = synth.make_segs(n, k, h, w, seed=n)
@@ -249,17 +260,14 @@ def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, monkeypatch, n, gro
 
 
 @pytest.mark.parametrize("n,sections", [(32, None), (5, None), (70, None), (9, "1"), (13, "64"), (1, None)])
-def test_host_frames_path(torch_cuda, oracle_mod, monkeypatch, n, sections):
+def test_host_frames_path(torch_cuda, oracle_mod, tuning, n, sections):
     """Frames left on the CPU in pinned memory (what the reference's trainer passes) take
     tcamcrf_loss_forward_host_frames: copied section by section on the library's copy stream while the lattice of
     the sections already in is built.  Same AS / loss as the oracle, for one and several chunks, ragged sections,
     the filter-only and the fused-softmax variants; pageable frames take the plain copy."""
     torch = torch_cuda
     from tcam_wsol_video_b200 import ops
-    if sections is None:
-        monkeypatch.delenv("TCAMCRF_HIMG_SECTIONS", raising=False)
-    else:
-        monkeypatch.setenv("TCAMCRF_HIMG_SECTIONS", sections)
+    tuning("HIMG_SECTIONS", sections)
     k, h, w = 3, 24, 20
     img = synth.make_images(n, h, w, "noise" if n % 2 else "natural", seed=90 + n)
     seg_np = synth.make_segs(n, k, h, w, seed=90 + n)
@@ -440,7 +448,7 @@ def test_adaptive_table_size_follows_the_frames(torch_cuda, oracle_mod, k):
 @pytest.mark.parametrize("kind", ["noise", "natural"])
 @pytest.mark.parametrize("k,dim,hw", [(10, 0, (40, 52)), (5, 0, (33, 35)), (7, 0, (24, 130)), (12, 0, (31, 37)),
                                       (16, 0, (40, 40)), (13, 3, (40, 44)), (9, 0, (1, 50))])
-def test_row_cooperative_kernels(torch_cuda, oracle_mod, monkeypatch, kind, k, dim, hw):
+def test_row_cooperative_kernels(torch_cuda, oracle_mod, tuning, kind, k, dim, hw):
     """splat_rows_kernel / slice_rows_kernel (the kernels the density hint selects for dense lattices, K = 5..16:
     neighbouring lanes share a vertex row) forced on with TCAMCRF_DENSE=1, against the oracle and against the
     per-pixel kernels (TCAMCRF_DENSE=0): every row width (2, 3, 4 float4s), ragged frames (pixel counts that are
@@ -462,7 +470,7 @@ def test_row_cooperative_kernels(torch_cuda, oracle_mod, monkeypatch, kind, k, d
     want_loss = -(seg_np.astype(np.float64) * want.astype(np.float64)).sum() / n
     out = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("TCAMCRF_DENSE", mode)
+        tuning("DENSE", mode)
         got, loss, _ = ops.crf_forward(torch.from_numpy(img), seg, cfg, check=True)
         _assert_close(got.cpu().numpy(), want, f"AS, TCAMCRF_DENSE={mode}")
         assert abs(loss.item() - want_loss) < REL_TOL * abs(want_loss)
@@ -635,3 +643,71 @@ def test_unusual_shapes(torch_cuda, oracle_mod, case):
         want = oracle_mod.port_bilateralfilter_batch(img, seg, n, k, h, w, 15.0, 100.0)
     got, _, _ = ops.crf_forward(torch.from_numpy(img), torch.from_numpy(seg).cuda(), cfg, want_loss=False, check=True)
     _assert_close(got.cpu().numpy(), want.reshape(seg.shape), case)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs at FULL size against the oracle
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+def test_full_size_config2_vs_reference(torch_cuda, oracle_mod, kind):
+    """BASELINE configs[1] as benchmarked -- 32 frames x 10 classes x 224^2 -- against the reference's own C++
+    (oracle/_ref, bilateralfilter.cpp:42-55, when it travelled to this box; else the C restatement): AS, loss
+    (dense_crf_loss.py:63-64) and gradient (:73) within rel 1e-4.  Three calls on one workspace: from the second
+    on the density hint is in, so noise frames take the row-cooperative splat."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLoss
+    n, k, h, w = 32, 10, 224, 224
+    img = synth.make_images(n, h, w, kind, seed=0)
+    seg_np = synth.make_segs(n, k, h, w, seed=0)
+    fn, _ = oracle_mod.best_filter(color=False)
+    want_loss, want_grad, want_as = oracle_mod.densecrf_loss_fwd_bwd(img, seg_np, 15.0, 100.0, 1.0, fn)
+    images = torch.from_numpy(img).cuda()
+    mod = DenseCRFLoss(weight=1.0, sigma_rgb=15.0, sigma_xy=100.0, scale_factor=1.0)
+    from tcam_wsol_video_b200 import ops
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    for call in range(3):
+        seg = torch.from_numpy(seg_np).cuda().requires_grad_(True)
+        loss = mod(images=images, segmentations=seg)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(want_loss)) < REL_TOL * abs(float(want_loss)), f"loss, call {call}"
+        _assert_close(seg.grad.cpu().numpy(), want_grad, f"grad, call {call} ({kind})")
+        got_as, _, _ = ops.crf_forward(images, seg.detach(), cfg, want_loss=False, check=True)
+        _assert_close(got_as.cpu().numpy(), want_as, f"AS, call {call} ({kind})")
+
+
+@pytest.mark.parametrize("kind", ["noise", "natural"])
+@pytest.mark.parametrize("channels,hw", [(1, (64, 64)), (1, (448, 448)), (2, (64, 64)), (2, (448, 448)),
+                                         (4, (64, 64)), (1, (37, 53))])
+def test_xy_lattices_of_other_dimensions(torch_cuda, oracle_mod, kind, channels, hw):
+    """BASELINE configs[3]'s "grayscale 3-D bilateralfilter" (features x, y, gray: TCAMCRF_FEAT_XY_RGB with one
+    image plane) and the 4-D / 6-D siblings, at 64^2 and 448^2, against Permutohedral::init / compute
+    (permutohedral.cpp:115-297, 507-572) on explicit features built with initializePermutohedral's arithmetic
+    (bilateralfilter.cpp:4-19)."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    h, w = hw
+    n, k = 2, 2
+    rgb = synth.make_images(n, h, w, kind, seed=13 + channels)
+    planes = rgb if channels <= 3 else np.concatenate([rgb, rgb[:, ::-1][:, :1] * 0.5 + 3.0], axis=1)
+    planes = np.ascontiguousarray(planes[:, :channels])
+    seg = synth.make_segs(n, k, h, w, seed=17)
+    want = np.stack([oracle_mod.port_filter_features(oracle_mod.xy_features(h, w, 100.0, planes[i], 15.0), seg[i])
+                     for i in range(n)]).reshape(seg.shape)
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, channels, 15.0, 100.0)
+    got, _, _ = ops.crf_forward(torch.from_numpy(planes).cuda(), torch.from_numpy(seg).cuda(), cfg,
+                                want_loss=False, check=True)
+    _assert_close(got.cpu().numpy(), want, f"xy + {channels} planes, {h}x{w}, {kind}")
+
+
+@pytest.mark.parametrize("dim", [4, 6])
+def test_colour_lattices_of_other_dimensions(torch_cuda, oracle_mod, dim):
+    """colorbilateralfilter with DIM = 4 and 6 image planes (one image: the batch function's 3-plane stride makes
+    N > 1 read overlapping windows, colorbilateralfilter.cpp:50)."""
+    k, h, w = 2, 40, 44
+    rng = np.random.default_rng(dim)
+    img = rng.integers(0, 256, size=(1, dim, h, w)).astype(np.float32)
+    seg = synth.make_segs(1, k, h, w, seed=dim)
+    want = oracle_mod.port_colorbilateralfilter_batch(img, seg, 1, k, h, w, 15.0, dim).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=dim)
+    _assert_close(got, want, f"colour lattice, DIM={dim}")

@@ -100,7 +100,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tcamcrf.h but not exported"
-    assert lib.tcamcrf_version() == 100
+    assert lib.tcamcrf_version() == 101
 
 
 def test_workspace_sizing_and_argument_validation():
@@ -246,3 +246,35 @@ def test_temporal_frame_pickers():
     assert tp.temporal_frames(frames, "f2", 1, tp.TIME_BEFORE_AFTER) == ["f1", "f2", "f3"]
     assert tp.temporal_frames(frames, "f2", 1, tp.TIME_AFTER) == ["f2", "f3"]
     assert tp.temporal_frames(frames, "f2", 3, tp.TIME_INSTANT) == ["f2"]
+
+
+def test_key_range_is_refused_on_the_host():
+    """A sigma too small for the lattice dimension (or more than 6 feature dimensions) is refused up front with a
+    clear message instead of coming back as a NaN loss; pure host arithmetic, no device needed."""
+    ok = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    _lib.require_key_range(ok, 224, 224)
+    _lib.require_key_range(_lib.make_config(_lib.FEAT_COLOR, 6, 1.0), 224, 224)
+    for bad in (_lib.make_config(_lib.FEAT_XY_RGB, 3, 0.05, 100.0),      # 12-bit fields of the 5-D lattice
+                _lib.make_config(_lib.FEAT_COLOR, 6, 0.5),               # 10-bit fields at d = 6
+                _lib.make_config(_lib.FEAT_COLOR, 7, 15.0),              # d > 6 does not fit one 64-bit key
+                _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 1e-4)):      # position term out of range
+        with pytest.raises(_lib.TcamCrfError, match="out of range"):
+            _lib.require_key_range(bad, 224, 224)
+
+
+def test_tuning_knobs_are_set_at_run_time():
+    """The TCAMCRF_* environment variables are read once; tests and sweeps change knobs through the C ABI."""
+    _lib.set_tuning("DENSE", 1)
+    _lib.set_tuning("TCAMCRF_HOST_GROUPS", 3)
+    _lib.set_tuning("DENSE", -1)
+    _lib.set_tuning("HOST_GROUPS", -1)
+    with pytest.raises(_lib.TcamCrfError, match="unknown tuning knob"):
+        _lib.set_tuning("NO_SUCH_KNOB", 1)
+
+
+def test_weight_is_folded_only_when_it_is_a_plain_number():
+    import torch
+    from tcam_wsol_video_b200.dense_crf_loss import _folded_weight
+    assert _folded_weight(2e-9) == 2e-9 and _folded_weight(3) == 3.0
+    assert _folded_weight(torch.tensor(2e-9)) is None and _folded_weight(0.0) is None
+    assert _folded_weight(True) is None and _folded_weight(float("nan")) is None
