@@ -39,6 +39,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -84,6 +85,7 @@ static int fail(int code, const char *fmt, ...)
 struct Tuning {
     int chunk = 0;            // TCAMCRF_CHUNK: frames per pass (sweeps)
     int dense = -1;           // TCAMCRF_DENSE: force the row-cooperative splat on (1) / off (0); -1 = density hint
+    int build_dedup = -1;     // TCAMCRF_BUILD_DEDUP: force the shared-memory dedup build on (1) / off (0); -1 = density hint
     int himg_sections = 0;    // TCAMCRF_HIMG_SECTIONS: sections of a chunk on the host-frames path
     int host_groups = 0;      // TCAMCRF_HOST_GROUPS: value-stage groups per chunk on the host-pointer path
     int host_section0 = 0;    // TCAMCRF_HOST_SECTION0: frames of the first section on the host-pointer path
@@ -100,6 +102,7 @@ static Tuning &tuning()
         Tuning x;
         x.chunk = env_int("TCAMCRF_CHUNK", 0);
         x.dense = env_int("TCAMCRF_DENSE", -1);
+        x.build_dedup = env_int("TCAMCRF_BUILD_DEDUP", -1);
         x.himg_sections = env_int("TCAMCRF_HIMG_SECTIONS", 0);
         x.host_groups = env_int("TCAMCRF_HOST_GROUPS", 0);
         x.host_section0 = env_int("TCAMCRF_HOST_SECTION0", 0);
@@ -435,10 +438,54 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
 #ifndef TCAMCRF_BUILD_MINBLOCKS
 #define TCAMCRF_BUILD_MINBLOCKS 5
 #endif
+// Front end shared by the two build kernels: the pixel's features (initializePermutohedral, bilateralfilter.cpp:4-19 /
+// colorbilateralfilter.cpp:4-15), its embedding, the d+1 packed keys of its simplex, and the barycentric weights,
+// which leave the registers right here.  Reads the caller's images only, so it runs ahead of griddepcontrol.wait (the
+// kernel in front of a build kernel is prepare_kernel, an ordinary launch: every earlier reader of bary[] has
+// completed before any block of this grid runs).  Returns false when a lattice coordinate leaves the key range.
+template <int D, typename ImgT>
+__device__ __forceinline__ bool build_front(const BuildParams &p, int n, int pix, bool valid, bool ghost,
+                                            unsigned long long (&key)[D + 1])
+{
+    using Codec = KeyCodec<D>;
+    float f[D];
+    const size_t img0 = (size_t)n * p.stride_planes * p.P + pix;
+    if (ghost) {
+#pragma unroll
+        for (int c = 0; c < D; c++) f[c] = 0.0f;
+    } else if (p.feat == TCAMCRF_FEAT_XY_RGB) {
+        const int row = pix / p.W, col = pix - row * p.W;
+        f[0] = __fdiv_rn((float)col, p.sigma_xy);
+        if (D > 1) f[1 < D ? 1 : 0] = __fdiv_rn((float)row, p.sigma_xy);
+#pragma unroll
+        for (int c = 2; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)(c - 2) * p.P), p.sigma_rgb);
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)c * p.P), p.sigma_rgb);
+    }
+    int z[D + 1], rank[D + 1];
+    float bary[D + 1];
+    const bool ok = embed_point<D>(f, p.ec, z, rank, bary);
+    if (!ok) {
+        // keep the fields well-formed; the whole call is poisoned through the status word
+#pragma unroll
+        for (int i = 0; i <= D; i++) {
+            z[i] = 0;
+            rank[i] = i;
+        }
+    }
+    Codec::pack_simplex(z, rank, key);
+    if (valid) {
+        const size_t base = (size_t)n * (D + 1) * p.P + pix;
+#pragma unroll
+        for (int r = 0; r <= D; r++) p.bary[base + (size_t)r * p.P] = bary[r];
+    }
+    return ok;
+}
+
 template <int D, typename ImgT>
 __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kernel(const BuildParams p)
 {
-    using Codec = KeyCodec<D>;
 #if TCAMCRF_BUILD_INTERLEAVE
     const int n = p.frame0 + blockIdx.x;
     const int pix = blockIdx.y * kThreads + threadIdx.x;
@@ -460,40 +507,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     bool ok = true;
 
     if (active) {
-        float f[D];
-        const size_t img0 = (size_t)n * p.stride_planes * p.P + pix;
-        if (ghost) {
-#pragma unroll
-            for (int c = 0; c < D; c++) f[c] = 0.0f;
-        } else if (p.feat == TCAMCRF_FEAT_XY_RGB) {
-            const int row = pix / p.W, col = pix - row * p.W;
-            f[0] = __fdiv_rn((float)col, p.sigma_xy);
-            if (D > 1) f[1 < D ? 1 : 0] = __fdiv_rn((float)row, p.sigma_xy);
-#pragma unroll
-            for (int c = 2; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)(c - 2) * p.P), p.sigma_rgb);
-        } else {
-#pragma unroll
-            for (int c = 0; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)c * p.P), p.sigma_rgb);
-        }
-        int z[D + 1], rank[D + 1];
-        float bary[D + 1];
-        ok = embed_point<D>(f, p.ec, z, rank, bary);
-        if (!ok) {
-            // keep the fields well-formed; the whole call is poisoned through the status word
-#pragma unroll
-            for (int i = 0; i <= D; i++) {
-                z[i] = 0;
-                rank[i] = i;
-            }
-        }
-        Codec::pack_simplex(z, rank, key);
-        // The weights leave the registers here, ahead of the wait: the kernel in front of this one (prepare_kernel)
-        // is an ordinary launch, so every earlier reader of bary[] has completed before any block of this grid runs.
-        if (valid) {
-            const size_t base = (size_t)n * (D + 1) * p.P + pix;
-#pragma unroll
-            for (int r = 0; r <= D; r++) p.bary[base + (size_t)r * p.P] = bary[r];
-        }
+        ok = build_front<D, ImgT>(p, n, pix, valid, ghost, key);
     } else {
 #pragma unroll
         for (int r = 0; r <= D; r++) key[r] = kEmptyKey;
@@ -521,7 +535,9 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     Entry *tab = p.table + (size_t)n * p.slots;
     const unsigned int mask1 = geom.slots1 - 1;
     unsigned int pend = 0;
-    unsigned int leaders = 0;        // 5 bits per remainder: the lane that heads this lane's run
+    // 5 bits per remainder: the lane that heads this lane's run (7 remainders at D = 6 need 35 bits)
+    using LeaderWord = typename std::conditional<(D + 1) * 5 <= 32, unsigned int, unsigned long long>::type;
+    LeaderWord leaders = 0;
     int slot[D + 1];                 // the slot being probed; once the key is resolved, the slot it lives in
     int vid[D + 1];                  // id field of the entry last probed = the vertex id once resolved (-1: unknown)
     unsigned long long cur[D + 1];
@@ -530,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
         const unsigned long long left = __shfl_up_sync(0xffffffffu, key[r], 1);
         const bool head = lane == 0 || left != key[r];
         const unsigned int heads = __ballot_sync(0xffffffffu, head);
-        leaders |= (unsigned int)(31 - __clz(heads & (0xffffffffu >> (31 - lane)))) << (5 * r);   // nearest head at or below
+        leaders |= (LeaderWord)(unsigned int)(31 - __clz(heads & (0xffffffffu >> (31 - lane)))) << (5 * r);   // nearest head at or below
         slot[r] = -1;
         vid[r] = -1;
         cur[r] = 0;
@@ -620,6 +636,154 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
         const int mine = vid[r] >= 0 ? -2 - vid[r] : (slot[r] < 0 ? -1 : (int)(n * p.slots + slot[r]));
         const int ref = __shfl_sync(0xffffffffu, mine, (int)((leaders >> (5 * r)) & 31u));
         if (valid) p.offset[base + (size_t)r * p.P] = ref;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Build kernel for SPARSE lattices (real frames: ~0.06 vertices per pixel, ~100 pixels per vertex).
+//
+// build_kernel spends most of its time between the embedding and the offset store: run detection, d+1 hashes,
+// lock-step probes of the frame table in L2, id allocation -- and on real frames nearly all of that work finds a key
+// some neighbouring pixel has just handled (the +-4 sensor noise makes equal keys ALTERNATE along a row, so runs of
+// equal keys are only ~2.5 lanes long while a block of 256 pixels holds a few dozen distinct vertices).  Here the
+// 256 x (d+1) keys of a block are first deduplicated in a shared-memory table (a hit is one LDS.64 and a compare),
+// only the block's DISTINCT keys go to the frame table in L2 (one thread per key, first probe inline), and the pixels
+// pick their result up from shared memory.  All of the shared-memory phase runs ahead of griddepcontrol.wait, i.e.
+// while prepare_kernel is still clearing the tables.  Same table protocol and the same results as build_kernel (ids
+// are a relabelling); the host picks per call from the density hint, like the splat variant.
+constexpr int kTileW = 32, kTileH = kThreads / 32;   // pixel tile of a build_dedup_kernel block
+
+template <int D>
+struct DedupTable {
+    // 256 x (D+1) keys at most; a power of two >= that (load <= 0.875 in the worst case, D = 6)
+    static constexpr int kSlots = (D <= 2) ? 1024 : 2048;
+    static constexpr unsigned int kShift = (D <= 2) ? 22 : 21;   // 32 - log2(kSlots)
+};
+
+template <int D, typename ImgT>
+__global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_dedup_kernel(const BuildParams p)
+{
+    constexpr int kSlots = DedupTable<D>::kSlots;
+    __shared__ unsigned long long s_key[kSlots];
+    __shared__ int s_val[kSlots];                         // what offset[] gets for the key in the same slot
+    __shared__ unsigned short s_list[kThreads * (D + 1)];   // occupied slots, in insertion order
+    __shared__ int s_count;
+    // A block is a TILE of 32 x 8 pixels (a warp = 32 neighbouring pixels of one row: coalesced like the linear
+    // mapping), not 256 consecutive pixels: a row sweeps through many lattice cells, a compact tile through few (the
+    // synthetic natural frames: 77 distinct keys per tile against 293 per 256-pixel run).  One extra block per frame
+    // carries the ghost pixel (see build_kernel) when there is one.
+#if TCAMCRF_BUILD_INTERLEAVE
+    const int n = p.frame0 + blockIdx.x;
+    const int tile = blockIdx.y;
+#else
+    const int n = p.frame0 + blockIdx.y;
+    const int tile = blockIdx.x;
+#endif
+    const int tiles_x = (p.W + kTileW - 1) / kTileW;
+    const int H = p.P / p.W;
+    const bool ghost_block = tile == tiles_x * ((H + kTileH - 1) / kTileH);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int px = tx * kTileW + (threadIdx.x & 31), py = ty * kTileH + (threadIdx.x >> 5);
+    const bool valid = !ghost_block && px < p.W && py < H;
+    const bool ghost = ghost_block && threadIdx.x == 0;
+    const int pix = valid ? py * p.W + px : p.P;
+    const bool active = valid || ghost;
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < kSlots; i += kThreads) s_key[i] = kEmptyKey;
+    if (threadIdx.x == 0) s_count = 0;
+
+    unsigned long long key[D + 1];
+    bool ok = true;
+    if (active) ok = build_front<D, ImgT>(p, n, pix, valid, ghost, key);
+    __syncthreads();
+
+    // phase 1: the block's distinct keys (shared memory only)
+    int myslot[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        myslot[r] = 0;
+        if (!active) continue;
+        unsigned int h = hash_slot(key[r], kHashMul1, DedupTable<D>::kShift);
+        while (true) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s_key + h);
+            if (cur == kEmptyKey) {
+                cur = atomicCAS(s_key + h, kEmptyKey, key[r]);
+                if (cur == kEmptyKey) {
+                    s_list[atomicAdd(&s_count, 1)] = (unsigned short)h;
+                    break;
+                }
+            }
+            if (cur == key[r]) break;
+            h = (h + 1) & (kSlots - 1);
+        }
+        myslot[r] = (int)h;
+    }
+    __syncthreads();
+    const int count = s_count;
+
+    // everything above reads the caller's images only; the tables are cleared by the previous kernel
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!ok) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_KEY_RANGE);
+    const TableGeom geom = effective_geom(p.geom, (unsigned int)p.ctrl[kCtrlEffSlots]);
+    Entry *tab = p.table + (size_t)n * p.slots;
+
+    // phase 2: one thread per distinct key goes to the frame table (the loop bound is uniform over the block)
+    bool table_full = false, spilled_any = false, pool_full = false;
+    for (int base = 0; base < count; base += kThreads) {
+        const int i = base + threadIdx.x;
+        const bool on = i < count;
+        int hs = 0, slot = -1, vid = -1;
+        unsigned long long k = kEmptyKey;
+        bool won = false;
+        if (on) {
+            hs = s_list[i];
+            k = s_key[hs];
+            const unsigned int h = hash_primary(k, geom);
+            unsigned long long cur;
+            load_entry_cg(tab + h, cur, vid);   // {key, id} in one 16-byte load
+            if (cur == k) {
+                slot = (int)h;   // the common case on real frames: an earlier block of the frame created it
+            } else {
+                bool spilled;
+                slot = table_insert_from(tab, geom, k, h, 0, cur, won, spilled);
+                vid = -1;        // ours to allocate below, or not looked at: the splat resolves the entry index
+                table_full |= slot < 0;
+                spilled_any |= spilled;
+            }
+        }
+        // warp-aggregated allocation of dense vertex ids: one atomic per warp on the frame's counter
+        const unsigned int winners = __ballot_sync(0xffffffffu, won);
+        if (winners) {
+            const int leader = __ffs(winners) - 1;
+            int wbase = 0;
+            if (lane == leader) wbase = atomicAdd(p.ctrl + kCtrlCounts + n, __popc(winners));
+            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+            if (won) {
+                const int local = wbase + __popc(winners & ((1u << lane) - 1u));
+                if (local < p.stride) {
+                    vid = n * p.stride + local;
+                    tab[slot].id = vid;
+                    p.vkey[vid] = k;
+                } else {
+                    pool_full = true;   // the entry's id stays -1
+                }
+            }
+        }
+        // -2 - id (vertex id known), the entry index (>= 0: the first splat looks the id up) or -1 (table full)
+        if (on) s_val[hs] = vid >= 0 ? -2 - vid : (slot < 0 ? -1 : (int)(n * p.slots + slot));
+    }
+    if (table_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_TABLE_FULL);
+    if (spilled_any) p.ctrl[kCtrlDirtyNew] = 1;
+    if (pool_full) atomicOr(p.ctrl + kCtrlStatus, TCAMCRF_DEV_POOL_FULL);
+    __syncthreads();
+
+    // phase 3: every pixel picks up the results for its keys
+    if (valid) {
+        const size_t base = (size_t)n * (D + 1) * p.P + pix;
+#pragma unroll
+        for (int r = 0; r <= D; r++) p.offset[base + (size_t)r * p.P] = s_val[myslot[r]];
     }
 }
 
@@ -1386,9 +1550,12 @@ static void launch_chained(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st,
 }
 
 template <int D, typename ImgT>
-static void launch_build(const BuildParams &bp, dim3 grid, cudaStream_t st)
+static void launch_build(const BuildParams &bp, dim3 grid, bool dedup, cudaStream_t st)
 {
-    launch_chained(build_kernel<D, ImgT>, grid, st, bp);
+    if (dedup)
+        launch_chained(build_dedup_kernel<D, ImgT>, grid, st, bp);
+    else
+        launch_chained(build_kernel<D, ImgT>, grid, st, bp);
 }
 
 template <int D, int V>
@@ -1459,6 +1626,12 @@ static void launch_blur(int V, const BlurParams &bp, int nc, cudaStream_t st)
     return launch_blur_kv<1, 1>(bp, nc, st);               // Kp = 1
 }
 
+static int density_hint(void *ws);   // largest per-frame vertex count seen lately on a workspace (0: unknown); below
+
+// "Dense" lattice: more than one vertex per four pixels in the fullest frame lately (iid-noise frames have ~1.1 per
+// pixel, real frames ~0.06).  Selects kernel variants that are both correct for every input.
+static bool lattice_is_dense(int hint, int P) { return (long long)hint * 4 > (long long)P; }
+
 // Stage 1 of a chunk: the lattice of `nc` frames (tables, per-pixel vertices and weights, blur links).  Needs
 // only the images.  `zero_values`: also clear the value rows in the same launch (the device path does; the
 // host path clears them group by group in value_stages).
@@ -1495,14 +1668,26 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         bp.frame0 = frame0;
         scale_factors(D, bp.ec);
 #if TCAMCRF_BUILD_INTERLEAVE
-        const dim3 bgrid(nc, pl.blocks_per_frame);
+        dim3 bgrid(nc, pl.blocks_per_frame);
 #else
-        const dim3 bgrid(pl.blocks_per_frame, nc);
+        dim3 bgrid(pl.blocks_per_frame, nc);
 #endif
+        // sparse lattice lately (or nothing known yet): deduplicate the block's keys in shared memory first
+        bool dedup = !lattice_is_dense(density_hint(ws), pl.P);
+        if (tuning().build_dedup >= 0) dedup = tuning().build_dedup != 0;   // tests and sweeps: force either way
+        if (dedup) {   // one block per 32 x 8 tile, + the ghost pixel's block
+            const unsigned int tiles = (unsigned int)(((pl.W + kTileW - 1) / kTileW) * ((pl.H + kTileH - 1) / kTileH)) +
+                                       ((pl.P & 3) != 0 ? 1u : 0u);
+#if TCAMCRF_BUILD_INTERLEAVE
+            bgrid = dim3(nc, tiles);
+#else
+            bgrid = dim3(tiles, nc);
+#endif
+        }
         if (u8)
-            launch_build<D, uint8_t>(bp, bgrid, st);
+            launch_build<D, uint8_t>(bp, bgrid, dedup, st);
         else
-            launch_build<D, float>(bp, bgrid, st);
+            launch_build<D, float>(bp, bgrid, dedup, st);
     }
     VertexParams vp;
     vp.table = table;
@@ -1671,7 +1856,7 @@ static int value_stages(const Plan &pl, const float *segs, float *as_out, int fr
     pp.Kp = pl.Kp;
     pp.frame0 = frame0;
     // dense lattice lately (more than one vertex per four pixels in the fullest frame): row-cooperative splat
-    pp.dense = (long long)density_hint(ws) * 4 > (long long)pl.P ? 1 : 0;
+    pp.dense = lattice_is_dense(density_hint(ws), pl.P) ? 1 : 0;
     if (tuning().dense >= 0) pp.dense = tuning().dense != 0;   // tests and sweeps: force either way
     pp.pool = pl.pool;
     pp.alpha = 1.0f / (1 + powf(2, -D));
@@ -2480,6 +2665,7 @@ int tcamcrf_set_tuning(const char *name, int value)
     Tuning &t = tuning();
     if (!strcmp(name, "CHUNK")) t.chunk = value > 0 ? value : 0;
     else if (!strcmp(name, "DENSE")) t.dense = value < 0 ? -1 : (value != 0);
+    else if (!strcmp(name, "BUILD_DEDUP")) t.build_dedup = value < 0 ? -1 : (value != 0);
     else if (!strcmp(name, "HIMG_SECTIONS")) t.himg_sections = value > 0 ? value : 0;
     else if (!strcmp(name, "HOST_GROUPS")) t.host_groups = value > 0 ? value : 0;
     else if (!strcmp(name, "HOST_SECTION0")) t.host_section0 = value > 0 ? value : 0;

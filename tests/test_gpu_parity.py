@@ -128,10 +128,14 @@ def _debug_lattice(cfg, img, h, w):
     return off.reshape(p, d + 1), bary.reshape(p, d + 1), M, nbr[: (d + 1) * M * 2].reshape(d + 1, M, 2)
 
 
+@pytest.mark.parametrize("build", ["0", "1"], ids=["build_kernel", "build_dedup_kernel"])
 @pytest.mark.parametrize("kind", ["noise", "natural"])
 @pytest.mark.parametrize("dim", [0, 3, 1])
 @pytest.mark.parametrize("hw", [(32, 40), (31, 37), (224, 224)])
-def test_lattice_structure_bit_exact(torch_cuda, oracle_mod, kind, dim, hw):
+def test_lattice_structure_bit_exact(torch_cuda, oracle_mod, tuning, kind, dim, hw, build):
+    """Both build kernels (lock-step probes per pixel / the block's distinct keys deduplicated in shared memory
+    first), forced through TCAMCRF_BUILD_DEDUP; the library picks between them from the density hint."""
+    tuning("BUILD_DEDUP", build)
     h, w = hw
     img = synth.make_images(1, h, w, kind, seed=21)[0]
     if dim:
@@ -386,11 +390,13 @@ def test_device_status_poisons_outputs(torch_cuda):
     assert st & _lib.DEV_KEY_RANGE and torch.isnan(loss).all()
 
 
+@pytest.mark.parametrize("build", ["0", "1"], ids=["build_kernel", "build_dedup_kernel"])
 @pytest.mark.parametrize("load", [0.25, 0.5, 0.9, 4.0, 64.0])
-def test_hash_load_factor_sweep(torch_cuda, oracle_mod, load):
+def test_hash_load_factor_sweep(torch_cuda, oracle_mod, tuning, load, build):
     """BASELINE config 4 (occupancy sweep): results do not depend on the table size.  Loads above ~1 make the
     primary tier smaller than the lattice, so most vertices live in the overflow tier."""
     torch = torch_cuda
+    tuning("BUILD_DEDUP", build)
     from tcam_wsol_video_b200 import ops
     n, k, h, w = 1, 2, 96, 96
     img = synth.make_images(n, h, w, "noise", seed=91)
@@ -401,10 +407,12 @@ def test_hash_load_factor_sweep(torch_cuda, oracle_mod, load):
     _assert_close(as_t.cpu().numpy(), want, f"load {load}")
 
 
-def test_overflow_tier_is_cleared_between_calls(torch_cuda, oracle_mod):
+@pytest.mark.parametrize("build", ["0", "1"], ids=["build_kernel", "build_dedup_kernel"])
+def test_overflow_tier_is_cleared_between_calls(torch_cuda, oracle_mod, tuning, build):
     """A call that spills into the overflow tier leaves keys there; the next call on the same workspace (same
     plan) must not see them.  Three different images back to back through a deliberately tiny primary tier."""
     torch = torch_cuda
+    tuning("BUILD_DEDUP", build)
     from tcam_wsol_video_b200 import ops
     n, k, h, w = 2, 2, 64, 80
     cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, hash_load=64.0)
@@ -679,12 +687,14 @@ def test_full_size_config2_vs_reference(torch_cuda, oracle_mod, kind):
 @pytest.mark.parametrize("kind", ["noise", "natural"])
 @pytest.mark.parametrize("channels,hw", [(1, (64, 64)), (1, (448, 448)), (2, (64, 64)), (2, (448, 448)),
                                          (4, (64, 64)), (1, (37, 53))])
-def test_xy_lattices_of_other_dimensions(torch_cuda, oracle_mod, kind, channels, hw):
+@pytest.mark.parametrize("build", ["0", "1"], ids=["build_kernel", "build_dedup_kernel"])
+def test_xy_lattices_of_other_dimensions(torch_cuda, oracle_mod, tuning, kind, channels, hw, build):
     """BASELINE configs[3]'s "grayscale 3-D bilateralfilter" (features x, y, gray: TCAMCRF_FEAT_XY_RGB with one
     image plane) and the 4-D / 6-D siblings, at 64^2 and 448^2, against Permutohedral::init / compute
     (permutohedral.cpp:115-297, 507-572) on explicit features built with initializePermutohedral's arithmetic
-    (bilateralfilter.cpp:4-19)."""
+    (bilateralfilter.cpp:4-19).  Both build kernels."""
     torch = torch_cuda
+    tuning("BUILD_DEDUP", build)
     from tcam_wsol_video_b200 import ops
     h, w = hw
     n, k = 2, 2
@@ -700,10 +710,12 @@ def test_xy_lattices_of_other_dimensions(torch_cuda, oracle_mod, kind, channels,
     _assert_close(got.cpu().numpy(), want, f"xy + {channels} planes, {h}x{w}, {kind}")
 
 
+@pytest.mark.parametrize("build", ["0", "1"], ids=["build_kernel", "build_dedup_kernel"])
 @pytest.mark.parametrize("dim", [4, 6])
-def test_colour_lattices_of_other_dimensions(torch_cuda, oracle_mod, dim):
+def test_colour_lattices_of_other_dimensions(torch_cuda, oracle_mod, tuning, dim, build):
     """colorbilateralfilter with DIM = 4 and 6 image planes (one image: the batch function's 3-plane stride makes
     N > 1 read overlapping windows, colorbilateralfilter.cpp:50)."""
+    tuning("BUILD_DEDUP", build)
     k, h, w = 2, 40, 44
     rng = np.random.default_rng(dim)
     img = rng.integers(0, 256, size=(1, dim, h, w)).astype(np.float32)
