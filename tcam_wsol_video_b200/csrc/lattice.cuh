@@ -230,6 +230,110 @@ __device__ __forceinline__ bool embed_point(const float (&f)[D], const EmbedCons
 }
 
 #if defined(__CUDACC__)
+// 1 << s as a 64-bit word for s in [0, 64); 0 for s >= 64.  PTX shl.b32 clamps the shift amount at the register
+// width, so the low word vanishes for s >= 32 and the high word for s < 32 (s - 32 wraps to a huge amount) and s = 64.
+__device__ __forceinline__ unsigned long long one_shifted(unsigned int s)
+{
+    unsigned int lo, hi;
+    asm("shl.b32 %0, 1, %1;" : "=r"(lo) : "r"(s));
+    asm("shl.b32 %0, 1, %1;" : "=r"(hi) : "r"(s - 32u));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// embed_point + KeyCodec::pack_simplex in one pass, for kernels that can spare a per-thread scratch column in shared
+// memory: `sf` (floats) and `si` (16-bit words) point at the calling thread's column of a [D+1][stride] array.  The
+// same arithmetic, operation for operation, as the two functions above (tests compare the kernels that use either);
+// what changes is how "the element with rank t" is found: the generic code selects it with (D+1)^2 compares (and
+// decodes the inverse permutation from nibbles with 64-bit variable shifts), here every element is stored at the row
+// its rank names and read back in order -- conflict-free (the column is the thread), ~110 instructions less at D = 5.
+// Returns false when a quotient leaves the packed-key range (keys and weights are then well-formed but meaningless).
+template <int D>
+__device__ __forceinline__ bool embed_simplex_scratch(const float (&f)[D], const EmbedConsts &ec, float *sf,
+                                                      unsigned short *si, int stride, unsigned long long (&key)[D + 1],
+                                                      float (&bary)[D + 1])
+{
+    using Codec = KeyCodec<D>;
+    constexpr float inv_dp1 = 1.0f / (D + 1);
+    constexpr float dp1 = (float)(D + 1);
+    float el[D + 1];
+    float sm = 0.0f;
+#pragma unroll
+    for (int j = D; j > 0; j--) {
+        const float cf = __fmul_rn(f[j - 1], ec.scale[j - 1]);
+        el[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
+        sm = __fadd_rn(sm, cf);
+    }
+    el[0] = sm;
+
+    int z[D + 1], rank[D + 1];
+    int sum = 0;
+    float res[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        const int vi = __float2int_rn(__fmul_rn(inv_dp1, el[i]));
+        z[i] = vi;
+        res[i] = __fsub_rn(el[i], __fmul_rn((float)vi, dp1));
+        sum += vi;
+    }
+    // rank[j] = #{i < j : res[i] >= res[j]} + #{k > j : res[j] < res[k]}  (the pairwise counts of embed_point)
+#pragma unroll
+    for (int i = 0; i <= D; i++) rank[i] = i;
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = i + 1; j <= D; j++) {
+            const int c = res[i] < res[j] ? 1 : 0;
+            rank[i] += c;
+            rank[j] -= c;
+        }
+    int zmin = 0x7fffffff, zmax = -0x7fffffff - 1, rmin = 0x7fffffff, rmax = -0x7fffffff - 1;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        rank[i] += sum;
+        if (rank[i] < 0) {
+            rank[i] += D + 1;
+            z[i] += 1;
+        } else if (rank[i] > D) {
+            rank[i] -= D + 1;
+            z[i] -= 1;
+        }
+        zmin = min(zmin, z[i]);
+        zmax = max(zmax, z[i]);
+        rmin = min(rmin, rank[i]);
+        rmax = max(rmax, rank[i]);
+    }
+    // q = z or z-1 must stay inside the field, with room for a neighbour step; a rank outside 0..D can only come
+    // from a non-finite feature
+    const bool in_range = (zmin - 1 >= Codec::kQMin) && (zmax <= Codec::kQMax) && rmin >= 0 && rmax <= D;
+    if (!in_range) {
+#pragma unroll
+        for (int i = 0; i <= D; i++) {
+            z[i] = 0;
+            rank[i] = i;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        sf[rank[i] * stride] = __fmul_rn(__fsub_rn(el[i], __fmul_rn((float)z[i], dp1)), inv_dp1);
+        // where coordinate i sits in the packed key (the implicit coordinate D has no field: shift 64 -> unit 0)
+        si[rank[i] * stride] = (unsigned short)(i < D ? Codec::kRemBits + i * Codec::kFieldBits : 64);
+    }
+    float vs[D + 1];
+#pragma unroll
+    for (int t = 0; t <= D; t++) vs[t] = sf[t * stride];
+#pragma unroll
+    for (int t = 1; t <= D; t++) bary[t] = __fsub_rn(vs[D - t], vs[D - t + 1]);
+    bary[0] = __fadd_rn(vs[D], __fadd_rn(1.0f, -vs[0]));
+
+    int q0[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) q0[i] = z[i];
+    key[0] = Codec::pack(q0, 0);
+#pragma unroll
+    for (int r = 1; r <= D; r++) key[r] = key[r - 1] + 1ull - one_shifted(si[(D + 1 - r) * stride]);
+    return in_range;
+}
+
 // ---------------------------------------------------------------------------
 // Two-tier open-addressing table (one per frame), 16-byte entries {key, id}.
 //

@@ -351,7 +351,7 @@ struct BuildParams {
     float *bary;            // [n][r][p]
     unsigned long long *vkey;   // [pool] key of each vertex
     int *ctrl;
-    int P, W;
+    int P, W, H;
     int stride_planes, channels, feat;
     TableGeom geom;
     unsigned int slots;
@@ -651,73 +651,121 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
 // pick their result up from shared memory.  All of the shared-memory phase runs ahead of griddepcontrol.wait, i.e.
 // while prepare_kernel is still clearing the tables.  Same table protocol and the same results as build_kernel (ids
 // are a relabelling); the host picks per call from the density hint, like the splat variant.
-constexpr int kTileW = 32, kTileH = kThreads / 32;   // pixel tile of a build_dedup_kernel block
+#ifndef TCAMCRF_TILE_W
+#define TCAMCRF_TILE_W 32
+#endif
+#ifndef TCAMCRF_TILE_H
+#define TCAMCRF_TILE_H 8
+#endif
+constexpr int kTileW = TCAMCRF_TILE_W, kTileH = TCAMCRF_TILE_H;   // pixel tile of a build_dedup_kernel block
+constexpr int kTileThreads = kTileW * kTileH;
+static_assert(kTileW == 8 || kTileW == 16 || kTileW == 32, "a warp covers whole row segments of the tile");
+static_assert(kTileThreads % 32 == 0 && kTileThreads <= 256, "tile = one thread block");
+
+constexpr int ceil_log2(int v) { return v <= 1 ? 0 : 1 + ceil_log2((v + 1) / 2); }
 
 template <int D>
 struct DedupTable {
-    // 256 x (D+1) keys at most; a power of two >= that (load <= 0.875 in the worst case, D = 6)
-    static constexpr int kSlots = (D <= 2) ? 1024 : 2048;
-    static constexpr unsigned int kShift = (D <= 2) ? 22 : 21;   // 32 - log2(kSlots)
+    // threads x (D+1) keys at most; the power of two >= that (load <= 0.875 in the worst case: 256 threads, D = 6)
+    static constexpr int kBits = ceil_log2(kTileThreads * (D + 1));
+    static constexpr int kSlots = 1 << kBits;
+    static constexpr unsigned int kShift = 32 - kBits;
 };
 
+#ifndef TCAMCRF_DEDUP_MINBLOCKS
+#define TCAMCRF_DEDUP_MINBLOCKS 8
+#endif
 template <int D, typename ImgT>
-__global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_dedup_kernel(const BuildParams p)
+__global__ void __launch_bounds__(kTileThreads, TCAMCRF_DEDUP_MINBLOCKS) build_dedup_kernel(const BuildParams p)
 {
     constexpr int kSlots = DedupTable<D>::kSlots;
-    __shared__ unsigned long long s_key[kSlots];
+    __shared__ __align__(16) unsigned long long s_key[kSlots];
     __shared__ int s_val[kSlots];                         // what offset[] gets for the key in the same slot
-    __shared__ unsigned short s_list[kThreads * (D + 1)];   // occupied slots, in insertion order
+    __shared__ unsigned short s_list[kTileThreads * (D + 1)];   // occupied slots, in insertion order
     __shared__ int s_count;
+    static_assert(kSlots >= kTileThreads * (D + 1), "the embedding scratch lives in s_val");
     // A block is a TILE of 32 x 8 pixels (a warp = 32 neighbouring pixels of one row: coalesced like the linear
     // mapping), not 256 consecutive pixels: a row sweeps through many lattice cells, a compact tile through few (the
-    // synthetic natural frames: 77 distinct keys per tile against 293 per 256-pixel run).  One extra block per frame
-    // carries the ghost pixel (see build_kernel) when there is one.
-#if TCAMCRF_BUILD_INTERLEAVE
+    // synthetic natural frames: 77 distinct keys per tile against 293 per 256-pixel run).  grid = (frames, tile rows
+    // [+ 1], tile columns); block (ty = tile rows, tx = 0) carries the ghost pixel (see build_kernel) when there is one.
     const int n = p.frame0 + blockIdx.x;
-    const int tile = blockIdx.y;
-#else
-    const int n = p.frame0 + blockIdx.y;
-    const int tile = blockIdx.x;
-#endif
-    const int tiles_x = (p.W + kTileW - 1) / kTileW;
-    const int H = p.P / p.W;
-    const bool ghost_block = tile == tiles_x * ((H + kTileH - 1) / kTileH);
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int px = tx * kTileW + (threadIdx.x & 31), py = ty * kTileH + (threadIdx.x >> 5);
-    const bool valid = !ghost_block && px < p.W && py < H;
-    const bool ghost = ghost_block && threadIdx.x == 0;
-    const int pix = valid ? py * p.W + px : p.P;
-    const bool active = valid || ghost;
     const int lane = threadIdx.x & 31;
+    const int px = blockIdx.z * kTileW + (threadIdx.x % kTileW), py = blockIdx.y * kTileH + (threadIdx.x / kTileW);
+    const bool ghost_block = (int)blockIdx.y * kTileH >= p.H;
+    if (ghost_block && blockIdx.z != 0) return;
+    const bool valid = !ghost_block && px < p.W && py < p.H;
+    const bool ghost = ghost_block && threadIdx.x == 0;
+    const bool active = valid || ghost;
+    const int pix = valid ? py * p.W + px : p.P;
 
-    for (int i = threadIdx.x; i < kSlots; i += kThreads) s_key[i] = kEmptyKey;
-    if (threadIdx.x == 0) s_count = 0;
-
+    // the pixel's features (initializePermutohedral, bilateralfilter.cpp:4-19 / colorbilateralfilter.cpp:4-15)
+    float f[D];
+#pragma unroll
+    for (int c = 0; c < D; c++) f[c] = 0.0f;
+    if (valid) {
+        const size_t img0 = (size_t)n * p.stride_planes * p.P + pix;
+        if (p.feat == TCAMCRF_FEAT_XY_RGB) {
+            f[0] = __fdiv_rn((float)px, p.sigma_xy);
+            if (D > 1) f[1 < D ? 1 : 0] = __fdiv_rn((float)py, p.sigma_xy);
+#pragma unroll
+            for (int c = 2; c < D; c++)
+                f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)(c - 2) * p.P), p.sigma_rgb);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) f[c] = __fdiv_rn(load_pixel<ImgT>(p.images, img0 + (size_t)c * p.P), p.sigma_rgb);
+        }
+    }
+    {   // clear the key table, two slots per store
+        const ulonglong2 empty2 = make_ulonglong2(kEmptyKey, kEmptyKey);
+        for (int i = threadIdx.x; i < kSlots / 2; i += kTileThreads) reinterpret_cast<ulonglong2 *>(s_key)[i] = empty2;
+        if (threadIdx.x == 0) s_count = 0;
+    }
+    // embedding, keys and weights; s_val / s_list are free until the barrier below and serve as the per-thread
+    // scratch columns of embed_simplex_scratch.  The weights leave the registers right here: the kernel in front of
+    // this one (prepare_kernel) is an ordinary launch, so every earlier reader of bary[] has completed.
     unsigned long long key[D + 1];
     bool ok = true;
-    if (active) ok = build_front<D, ImgT>(p, n, pix, valid, ghost, key);
+    if (active) {
+        float bary[D + 1];
+        ok = embed_simplex_scratch<D>(f, p.ec, reinterpret_cast<float *>(s_val) + threadIdx.x, s_list + threadIdx.x,
+                                      kTileThreads, key, bary);
+        if (valid) {
+            const size_t base = (size_t)n * (D + 1) * p.P + pix;
+#pragma unroll
+            for (int r = 0; r <= D; r++) p.bary[base + (size_t)r * p.P] = bary[r];
+        }
+    }
     __syncthreads();
 
     // phase 1: the block's distinct keys (shared memory only)
     int myslot[D + 1];
 #pragma unroll
     for (int r = 0; r <= D; r++) {
-        myslot[r] = 0;
-        if (!active) continue;
-        unsigned int h = hash_slot(key[r], kHashMul1, DedupTable<D>::kShift);
-        while (true) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s_key + h);
-            if (cur == kEmptyKey) {
-                cur = atomicCAS(s_key + h, kEmptyKey, key[r]);
+        unsigned int h = 0;
+        bool won = false;
+        if (active) {
+            h = hash_slot(key[r], kHashMul1, DedupTable<D>::kShift);
+            while (true) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s_key + h);
                 if (cur == kEmptyKey) {
-                    s_list[atomicAdd(&s_count, 1)] = (unsigned short)h;
-                    break;
+                    cur = atomicCAS(s_key + h, kEmptyKey, key[r]);
+                    won = cur == kEmptyKey;
+                    if (won) break;
                 }
+                if (cur == key[r]) break;
+                h = (h + 1) & (kSlots - 1);
             }
-            if (cur == key[r]) break;
-            h = (h + 1) & (kSlots - 1);
         }
         myslot[r] = (int)h;
+        // the slots this warp has just filled join the block's list: one shared-memory atomic per warp
+        const unsigned int w = __ballot_sync(0xffffffffu, won);
+        if (w) {
+            const int leader = __ffs(w) - 1;
+            int at = 0;
+            if (lane == leader) at = atomicAdd(&s_count, __popc(w));   // one lane: nothing for the compiler to aggregate
+            at = __shfl_sync(0xffffffffu, at, leader);
+            if (won) s_list[at + __popc(w & ((1u << lane) - 1u))] = (unsigned short)h;
+        }
     }
     __syncthreads();
     const int count = s_count;
@@ -731,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_dedup
 
     // phase 2: one thread per distinct key goes to the frame table (the loop bound is uniform over the block)
     bool table_full = false, spilled_any = false, pool_full = false;
-    for (int base = 0; base < count; base += kThreads) {
+    for (int base = 0; base < count; base += kTileThreads) {
         const int i = base + threadIdx.x;
         const bool on = i < count;
         int hs = 0, slot = -1, vid = -1;
@@ -1533,12 +1581,12 @@ static void scale_factors(int d, EmbedConsts &ec)
 
 // Launches `kernel` as a programmatic dependent of the previous kernel on `st` (see pdl_wait above).
 template <typename... KArgs, typename... Args>
-static void launch_chained(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args &&...args)
+static void launch_chained_block(void (*kernel)(KArgs...), dim3 grid, int threads, cudaStream_t st, Args &&...args)
 {
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = grid;
-    lc.blockDim = dim3(kThreads);
+    lc.blockDim = dim3(threads);
     lc.dynamicSmemBytes = 0;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1548,12 +1596,17 @@ static void launch_chained(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st,
     lc.numAttrs = 1;
     cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
 }
+template <typename... KArgs, typename... Args>
+static void launch_chained(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args &&...args)
+{
+    launch_chained_block(kernel, grid, kThreads, st, std::forward<Args>(args)...);
+}
 
 template <int D, typename ImgT>
 static void launch_build(const BuildParams &bp, dim3 grid, bool dedup, cudaStream_t st)
 {
     if (dedup)
-        launch_chained(build_dedup_kernel<D, ImgT>, grid, st, bp);
+        launch_chained_block(build_dedup_kernel<D, ImgT>, grid, kTileThreads, st, bp);
     else
         launch_chained(build_kernel<D, ImgT>, grid, st, bp);
 }
@@ -1656,6 +1709,7 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         bp.ctrl = ctrl;
         bp.P = pl.P;
         bp.W = pl.W;
+        bp.H = pl.H;
         bp.stride_planes = cfg->image_stride_planes;
         bp.channels = cfg->channels;
         bp.feat = cfg->feat;
@@ -1675,15 +1729,8 @@ static int lattice_stages(const tcamcrf_config *cfg, const Plan &pl, bool u8, co
         // sparse lattice lately (or nothing known yet): deduplicate the block's keys in shared memory first
         bool dedup = !lattice_is_dense(density_hint(ws), pl.P);
         if (tuning().build_dedup >= 0) dedup = tuning().build_dedup != 0;   // tests and sweeps: force either way
-        if (dedup) {   // one block per 32 x 8 tile, + the ghost pixel's block
-            const unsigned int tiles = (unsigned int)(((pl.W + kTileW - 1) / kTileW) * ((pl.H + kTileH - 1) / kTileH)) +
-                                       ((pl.P & 3) != 0 ? 1u : 0u);
-#if TCAMCRF_BUILD_INTERLEAVE
-            bgrid = dim3(nc, tiles);
-#else
-            bgrid = dim3(tiles, nc);
-#endif
-        }
+        if (dedup)   // one block per 32 x 8 tile; one more row of blocks for the ghost pixel's block
+            bgrid = dim3(nc, (pl.H + kTileH - 1) / kTileH + ((pl.P & 3) != 0 ? 1 : 0), (pl.W + kTileW - 1) / kTileW);
         if (u8)
             launch_build<D, uint8_t>(bp, bgrid, dedup, st);
         else
