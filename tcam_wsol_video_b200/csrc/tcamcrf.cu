@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <type_traits>
 #include <utility>
@@ -90,6 +91,9 @@ struct Tuning {
     int host_groups = 0;      // TCAMCRF_HOST_GROUPS: value-stage groups per chunk on the host-pointer path
     int host_section0 = 0;    // TCAMCRF_HOST_SECTION0: frames of the first section on the host-pointer path
     int host_trace = 0;       // TCAMCRF_HOST_TRACE: print the timeline of host_run
+    int host_taper = -1;      // TCAMCRF_HOST_TAPER: group = 1/taper of the frames left (0: equal groups; -1: default)
+    int host_graph = 1;       // TCAMCRF_HOST_GRAPH: replay the host-pointer schedule as a CUDA graph (pinned buffers)
+    int host_grow = 0;        // TCAMCRF_HOST_GROW: each section of the host-pointer path is this many times the one before
 };
 static int env_int(const char *name, int dflt)
 {
@@ -107,6 +111,9 @@ static Tuning &tuning()
         x.host_groups = env_int("TCAMCRF_HOST_GROUPS", 0);
         x.host_section0 = env_int("TCAMCRF_HOST_SECTION0", 0);
         x.host_trace = getenv("TCAMCRF_HOST_TRACE") != nullptr;
+        x.host_taper = env_int("TCAMCRF_HOST_TAPER", -1);
+        x.host_graph = env_int("TCAMCRF_HOST_GRAPH", 1);
+        x.host_grow = env_int("TCAMCRF_HOST_GROW", 0);
         return x;
     }();
     return t;
@@ -2102,8 +2109,21 @@ struct HostCtx {
     cudaStream_t s_in = nullptr;     // host -> device copies
     cudaStream_t s_out = nullptr;    // device -> host copies
     std::vector<cudaEvent_t> events;
+    void *pin = nullptr;             // pinned staging: grad_out in, per-group losses and status words out
+    size_t pin_cap = 0;
 };
 static HostCtx g_host_dev[kMaxDevices];
+
+static int host_pin_reserve(HostCtx &g_host, size_t bytes)
+{
+    if (g_host.pin_cap >= bytes) return TCAMCRF_OK;
+    if (g_host.pin) cudaFreeHost(g_host.pin);
+    g_host.pin = nullptr;
+    g_host.pin_cap = 0;
+    CUDA_TRY(cudaHostAlloc(&g_host.pin, bytes * 2, cudaHostAllocDefault));
+    g_host.pin_cap = bytes * 2;
+    return TCAMCRF_OK;
+}
 
 static int host_reserve(HostCtx &g_host, size_t bytes, char **out)
 {
@@ -2137,12 +2157,22 @@ struct HostTrace {
     struct Mark { const char *what; int idx; cudaEvent_t ev; };
     std::vector<Mark> marks;
     cudaEvent_t t0 = nullptr;
+    struct timespec h0;
     void begin(cudaStream_t s)
     {
         on = tuning().host_trace != 0;
         if (!on) return;
         cudaEventCreate(&t0);
         cudaEventRecord(t0, s);
+        clock_gettime(CLOCK_MONOTONIC, &h0);
+    }
+    // host wall clock since begin(): how long the CPU took to get here (enqueueing is not free)
+    void host_mark(const char *what)
+    {
+        if (!on) return;
+        struct timespec h1;
+        clock_gettime(CLOCK_MONOTONIC, &h1);
+        fprintf(stderr, "[host trace] %-12s host %7.3f ms\n", what, (h1.tv_sec - h0.tv_sec) * 1e3 + (h1.tv_nsec - h0.tv_nsec) * 1e-6);
     }
     void mark(const char *what, int idx, cudaStream_t s)
     {
@@ -2178,140 +2208,339 @@ static int check_device()
 // still work, the copies are then staged by the driver).
 //
 // The lattice depends on the images only, and the images are the small input (12 bytes per pixel against 4K
-// for the segmentations).  So the images of the whole batch go first, the lattice of the whole batch is built
-// in one full-width pass while the segmentations are still on the wire, and only the value stages (splat, blur,
-// slice, gradient) run group by group as the segmentations of a group arrive; the results of a group go back
-// while the next group computes.  The PCIe link is the bound of this path: the kernels hide behind it.
-static int host_run(const tcamcrf_config *cfg_in, const float *images, const float *segs, float *as_host,
-                    float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out)
-{
-    int rc = check_device();
-    if (rc) return rc;
-    if (!cfg_in || !images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
-    tcamcrf_config cfg = *cfg_in;
-    if (cfg.chunk_frames <= 0 || cfg.chunk_frames > 64) cfg.chunk_frames = 64;
+// for the segmentations).  So the images go first, the lattice is built while the segmentations are still on the
+// wire, and only the value stages (splat, blur, slice, gradient) run group by group as the segmentations of a group
+// arrive; the results of a group go back while the next group computes.  The PCIe link is the bound of this path
+// (one step's bytes in, one step's bytes out): what is left on top of it is the tail -- value stages and copy back
+// of the LAST group -- so the groups shrink towards the end of the batch.
+//
+// One call is ~200 driver calls (copies, events, ~130 launches): about as long on the CPU as the link needs for the
+// bytes.  With pinned buffers the whole schedule is therefore captured ONCE into a CUDA graph, keyed by the problem
+// and the buffer addresses, and a call is one graph launch (HostGraphs below).
+struct HostJob {
+    tcamcrf_config cfg;
     Plan pl;
-    rc = make_plan(&cfg, N, K, H, W, pl);
-    if (rc) return rc;
-    // groups of frames per chunk for the value stages (measured on B200, tools/e2e_sweep.sh)
-    int want_groups = K >= 6 ? 8 : 2;
-    if (tuning().host_groups >= 1 && tuning().host_groups <= 64) want_groups = tuning().host_groups;
-    int group = (pl.chunk + want_groups - 1) / want_groups;
-    if (group < 1) group = 1;
-    const int ngroups = N;   // upper bound: a group holds at least one frame
-    HostCtx &g_host = g_host_dev[current_device_slot()];
-    std::lock_guard<std::mutex> lock(g_host.mu);
-    const size_t P = (size_t)H * W;
-    const size_t img_frame = (size_t)cfg.image_stride_planes * P;   // floats per image
-    const size_t seg_frame = (size_t)K * P;
-    const size_t img_bytes = align_up((size_t)N * img_frame * sizeof(float), 256);
-    const size_t seg_bytes = align_up((size_t)N * seg_frame * sizeof(float), 256);
-    const size_t scal_bytes = align_up((size_t)(2 * ngroups + 2) * sizeof(float), 256);
-    char *base = nullptr;
-    rc = host_reserve(g_host, img_bytes + 3 * seg_bytes + scal_bytes + pl.total, &base);
-    if (rc) return rc;
-    float *d_img = (float *)base;
-    float *d_seg = (float *)(base + img_bytes);
-    float *d_as = (float *)(base + img_bytes + seg_bytes);
-    float *d_grad = (float *)(base + img_bytes + 2 * seg_bytes);
-    float *d_scal = (float *)(base + img_bytes + 3 * seg_bytes);  // [0]=grad_out, [1..]=loss per group, then status
-    float *d_loss = d_scal + 1;
-    int *d_status = (int *)(d_scal + 1 + ngroups);
-    char *d_ws = base + img_bytes + 3 * seg_bytes + scal_bytes;
-    cudaStream_t st = g_host.stream, s_in = g_host.s_in, s_out = g_host.s_out;
+    const float *images, *segs;
+    float *as_host, *grad_host;
+    bool want_loss;
+    int N, K, H, W;
+    // device buffers (inside g_host.buf) and pinned staging (g_host.pin)
+    float *d_img, *d_seg, *d_as, *d_grad, *d_scal, *d_loss;
+    int *d_status;
+    char *d_ws;
+    float *h_gout;      // pinned: grad_out of this call
+    float *h_loss;      // pinned: per-group losses
+    int *h_status;      // pinned: per-group status words
+    int max_groups;
+    bool dedup_hint, dense_hint;   // part of the graph key: the kernel variants are chosen at enqueue time
+};
 
-    HostTrace trace;
-    trace.begin(s_in);
-    if (grad_host) CUDA_TRY(cudaMemcpyAsync(d_scal, &grad_out, sizeof(float), cudaMemcpyHostToDevice, s_in));
-    int gi = 0;   // running group index
+// group sizes of the value stages for `frames` frames: equal groups (`taper` <= 0) or each group a 1/taper share of
+// what is left (at least one frame), so the last groups -- whose compute and copy back nothing overlaps -- are small
+static void host_groups(int frames, int equal_size, int taper, std::vector<int> &out)
+{
+    out.clear();
+    int left = frames;
+    while (left > 0) {
+        int g = taper > 0 ? (left + taper - 1) / taper : equal_size;
+        if (g < 1) g = 1;
+        if (g > left) g = left;
+        out.push_back(g);
+        left -= g;
+    }
+}
+
+// Queues the whole call on the three streams.  `st` is the origin: s_in / s_out fork from it and join it again, so
+// the same code runs eagerly or under stream capture.  `groups_out`: number of groups (entries of h_loss / h_status).
+static int host_enqueue(HostCtx &g_host, const HostJob &j, HostTrace &trace, int *groups_out)
+{
+    const Plan &pl = j.pl;
+    const int N = j.N, K = j.K;
+    cudaStream_t st = g_host.stream, s_in = g_host.s_in, s_out = g_host.s_out;
+    const size_t P = (size_t)j.H * j.W;
+    const size_t img_frame = (size_t)j.cfg.image_stride_planes * P;   // floats per image
+    const size_t seg_frame = (size_t)K * P;
     size_t ev_i = 0;
+    int rc;
+    cudaEvent_t ev_fork;
+    rc = host_event(g_host, ev_i++, &ev_fork);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(s_in, ev_fork, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s_out, ev_fork, 0));
+    if (j.grad_host) CUDA_TRY(cudaMemcpyAsync(j.d_scal, j.h_gout, sizeof(float), cudaMemcpyHostToDevice, s_in));
+    // Value-stage groups (measured on B200, tools/r2_host_sweep.sh, 32 frames): wide batches (K >= 6: the
+    // segmentations are most of the bytes) in groups of 2 frames, so that results flow back almost as soon as their
+    // inputs are in (K=10: 2.18 -> 2.06 ms per call); narrow ones in groups of a quarter chunk.  TCAMCRF_HOST_GROUPS
+    // = groups per chunk; TCAMCRF_HOST_TAPER > 0 = each group 1/taper of what is left.
+    int group = K >= 6 ? 2 : (pl.chunk + 3) / 4;
+    if (tuning().host_groups >= 1 && tuning().host_groups <= 64)
+        group = (pl.chunk + tuning().host_groups - 1) / tuning().host_groups;
+    if (group < 1) group = 1;
+    const int taper = tuning().host_taper >= 0 ? tuning().host_taper : 0;
+    std::vector<int> sizes;
+    int gi = 0;   // running group index
     for (int c0 = 0; c0 < N; c0 += pl.chunk) {
         const int cn = (N - c0) < pl.chunk ? (N - c0) : pl.chunk;
         // status word + loss accumulator start clean (MAGIC / DIRTY persist with the workspace)
-        CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(j.d_ws + pl.off_ctrl, 0, kCtrlResetInts * sizeof(int), st));
         // Sections: the lattice of a first, small section is built as soon as its images are in, so that the first
-        // results start their way back early -- the copy back runs at link speed from then on and is what ends
-        // last.  The rest of the chunk forms the second section (built at full width).
-        // Measured on B200, 32 frames (frames/s): K=10: one section 14.6 k, first section 4 frames 15.1 k;
-        // K=2: one section 28.2 k, first section 16 frames 32.5 k.
-        int sec0 = cn >= 16 ? (K >= 6 ? (cn + 7) / 8 : (cn + 1) / 2) : cn;
+        // results start their way back early (the link carries ~55 GB/s one way but only ~88 GB/s both ways together:
+        // every millisecond in which nothing flows back is lost); later sections grow by `grow` (their lattices are
+        // built at greater width while the segmentations of the section before are on the wire).
+        // Measured (32 frames): K=10: first section 4 frames, doubling (4, 8, 16, 4); K=2: four equal sections.
+        int sec0 = cn >= 16 ? (K >= 6 ? (cn + 7) / 8 : (cn + 3) / 4) : cn;
         if (tuning().host_section0 >= 1) sec0 = tuning().host_section0 < cn ? tuning().host_section0 : cn;
-        for (int f0 = 0, fn = 0; f0 < cn; f0 += fn) {
-            fn = f0 == 0 ? sec0 : cn - f0;
+        const int grow = tuning().host_grow >= 1 ? tuning().host_grow : (K >= 6 ? 2 : 1);
+        for (int f0 = 0, fn = 0, want = sec0; f0 < cn; f0 += fn) {
+            fn = want < cn - f0 ? want : cn - f0;
+            want = (long long)want * grow > cn ? cn : want * grow;
             cudaEvent_t ev_img;
             rc = host_event(g_host, ev_i++, &ev_img);
             if (rc) return rc;
             // only the planes the kernels read: the very last image may be shorter than the stride
             // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
             size_t img_floats = (size_t)fn * img_frame;
-            if (c0 + f0 + fn == N) img_floats = ((size_t)(fn - 1) * cfg.image_stride_planes + cfg.channels) * P;
-            CUDA_TRY(cudaMemcpyAsync(d_img + (size_t)(c0 + f0) * img_frame, images + (size_t)(c0 + f0) * img_frame,
+            if (c0 + f0 + fn == N) img_floats = ((size_t)(fn - 1) * j.cfg.image_stride_planes + j.cfg.channels) * P;
+            CUDA_TRY(cudaMemcpyAsync(j.d_img + (size_t)(c0 + f0) * img_frame, j.images + (size_t)(c0 + f0) * img_frame,
                                      img_floats * sizeof(float), cudaMemcpyHostToDevice, s_in));
             CUDA_TRY(cudaEventRecord(ev_img, s_in));
             trace.mark("images in", c0 + f0, s_in);
             CUDA_TRY(cudaStreamWaitEvent(st, ev_img, 0));
-            rc = run_lattice(&cfg, pl, false, d_img + (size_t)c0 * img_frame, f0, fn, d_ws, false, st);
+            rc = run_lattice(&j.cfg, pl, false, j.d_img + (size_t)c0 * img_frame, f0, fn, j.d_ws, false, st);
             if (rc) return rc;
             trace.mark("lattice", c0 + f0, st);
-            for (int g0 = f0, nc = 0; g0 < f0 + fn; g0 += nc, gi++) {
+            host_groups(fn, group, taper, sizes);
+            if (f0 == 0 && fn < cn && fn <= group) sizes.assign(1, fn);   // a small first section stays whole
+            int g0 = f0;
+            for (size_t si = 0; si < sizes.size(); si++, gi++) {
+                const int nc = sizes[si];
                 const int n0 = c0 + g0;
-                const int left = f0 + fn - g0;
-                nc = left < group ? left : group;
+                if (gi >= j.max_groups) return fail(TCAMCRF_ERR_INVALID, "internal: group count");
                 cudaEvent_t ev_in, ev_done;
                 rc = host_event(g_host, ev_i++, &ev_in);
                 if (rc) return rc;
                 rc = host_event(g_host, ev_i++, &ev_done);
                 if (rc) return rc;
-                CUDA_TRY(cudaMemcpyAsync(d_seg + n0 * seg_frame, segs + n0 * seg_frame,
+                CUDA_TRY(cudaMemcpyAsync(j.d_seg + n0 * seg_frame, j.segs + n0 * seg_frame,
                                          (size_t)nc * seg_frame * sizeof(float), cudaMemcpyHostToDevice, s_in));
                 CUDA_TRY(cudaEventRecord(ev_in, s_in));
                 trace.mark("segs in", gi, s_in);
                 CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
                 // every group reports its own share of the loss (already divided by the full batch size N)
-                CUDA_TRY(cudaMemsetAsync(d_ws + pl.off_acc, 0, sizeof(double), st));
-                rc = run_values(pl, d_seg + n0 * seg_frame, d_as + n0 * seg_frame, g0, nc, d_ws, true,
-                                loss_host != nullptr, loss_host ? d_loss + gi : nullptr, (float)N, 0, st);
+                CUDA_TRY(cudaMemsetAsync(j.d_ws + pl.off_acc, 0, sizeof(double), st));
+                rc = run_values(pl, j.d_seg + n0 * seg_frame, j.d_as + n0 * seg_frame, g0, nc, j.d_ws, true, j.want_loss,
+                                j.want_loss ? j.d_loss + gi : nullptr, (float)N, 0, st);
                 if (rc) return rc;
-                CUDA_TRY(cudaMemcpyAsync(d_status + gi, d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
-                if (grad_host) {
+                CUDA_TRY(cudaMemcpyAsync(j.d_status + gi, j.d_ws + pl.off_ctrl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                if (j.grad_host) {
                     StageScope scope(kStBackward, 1, st);
                     const size_t count = (size_t)nc * seg_frame;
                     size_t blocks = (count / 4 + kThreads - 1) / kThreads;
                     if (blocks > (size_t)sm_count() * 8) blocks = (size_t)sm_count() * 8;
                     if (blocks < 1) blocks = 1;
-                    loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_as + n0 * seg_frame, d_scal,
-                                                                                d_grad + n0 * seg_frame, count, (float)N,
+                    loss_backward_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(j.d_as + n0 * seg_frame, j.d_scal,
+                                                                                j.d_grad + n0 * seg_frame, count, (float)N,
                                                                                 1.0f);
                 }
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaEventRecord(ev_done, st));
                 trace.mark("computed", gi, st);
                 CUDA_TRY(cudaStreamWaitEvent(s_out, ev_done, 0));
-                if (as_host)
-                    CUDA_TRY(cudaMemcpyAsync(as_host + n0 * seg_frame, d_as + n0 * seg_frame,
+                if (j.as_host)
+                    CUDA_TRY(cudaMemcpyAsync(j.as_host + n0 * seg_frame, j.d_as + n0 * seg_frame,
                                              (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-                if (grad_host)
-                    CUDA_TRY(cudaMemcpyAsync(grad_host + n0 * seg_frame, d_grad + n0 * seg_frame,
+                if (j.grad_host)
+                    CUDA_TRY(cudaMemcpyAsync(j.grad_host + n0 * seg_frame, j.d_grad + n0 * seg_frame,
                                              (size_t)nc * seg_frame * sizeof(float), cudaMemcpyDeviceToHost, s_out));
                 trace.mark("results out", gi, s_out);
+                g0 += nc;
             }
         }
     }
-    std::vector<float> losses(gi, 0.f);
-    std::vector<int> status(gi, 0);
-    if (loss_host)
-        CUDA_TRY(cudaMemcpyAsync(losses.data(), d_loss, gi * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, gi * sizeof(int), cudaMemcpyDeviceToHost, st));
+    // per-group losses and status words into pinned staging, then join the copy streams
+    if (j.want_loss) CUDA_TRY(cudaMemcpyAsync(j.h_loss, j.d_loss, gi * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(j.h_status, j.d_status, gi * sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t ev_join_in, ev_join_out;
+    rc = host_event(g_host, ev_i++, &ev_join_in);
+    if (rc) return rc;
+    rc = host_event(g_host, ev_i++, &ev_join_out);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev_join_in, s_in));
+    CUDA_TRY(cudaEventRecord(ev_join_out, s_out));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_join_in, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_join_out, 0));
+    *groups_out = gi;
+    return TCAMCRF_OK;
+}
+
+// Captured schedules of host_run, a handful per device (a trainer alternates between a few pinned buffers).
+struct HostGraphs {
+    struct Key {
+        tcamcrf_config cfg;
+        int N, K, H, W;
+        const void *images, *segs, *as_host, *grad_host, *buf, *pin;
+        int want_loss, dedup, dense, groups_knob, taper_knob, sec0_knob, grow_knob;
+        bool operator==(const Key &o) const { return memcmp(this, &o, sizeof(Key)) == 0; }
+    };
+    struct Item {
+        Key key;
+        cudaGraphExec_t exec;
+        int groups;
+        long long launches;      // kernels of one replay (for tcamcrf_launch_count)
+        unsigned long long used;
+    };
+    std::vector<Item> items;
+    unsigned long long tick = 0;
+    void clear()
+    {
+        for (auto &it : items) cudaGraphExecDestroy(it.exec);
+        items.clear();
+    }
+};
+static HostGraphs g_host_graphs[kMaxDevices];
+
+static bool host_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int host_run(const tcamcrf_config *cfg_in, const float *images, const float *segs, float *as_host,
+                    float *loss_host, float *grad_host, int N, int K, int H, int W, float grad_out)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!cfg_in || !images || !segs) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    HostJob j;
+    j.cfg = *cfg_in;
+    if (j.cfg.chunk_frames <= 0 || j.cfg.chunk_frames > 64) j.cfg.chunk_frames = 64;
+    rc = make_plan(&j.cfg, N, K, H, W, j.pl);
+    if (rc) return rc;
+    const Plan &pl = j.pl;
+    const int dev = current_device_slot();
+    HostCtx &g_host = g_host_dev[dev];
+    HostGraphs &graphs = g_host_graphs[dev];
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    const int ngroups = N + 8;   // upper bound: a group holds at least one frame
+    const size_t P = (size_t)H * W;
+    const size_t img_frame = (size_t)j.cfg.image_stride_planes * P;
+    const size_t seg_frame = (size_t)K * P;
+    const size_t img_bytes = align_up((size_t)N * img_frame * sizeof(float), 256);
+    const size_t seg_bytes = align_up((size_t)N * seg_frame * sizeof(float), 256);
+    const size_t scal_bytes = align_up((size_t)(2 * ngroups + 2) * sizeof(float), 256);
+    char *base = nullptr;
+    const void *old_buf = g_host.buf;
+    rc = host_reserve(g_host, img_bytes + 3 * seg_bytes + scal_bytes + pl.total, &base);
+    if (rc) return rc;
+    if (old_buf != g_host.buf) graphs.clear();   // the captured schedules point into the old buffer
+    rc = host_pin_reserve(g_host, (size_t)(2 * ngroups + 2) * sizeof(float));
+    if (rc) return rc;   // (a new staging block changes the graph key: stale schedules age out of the cache)
+    j.images = images;
+    j.segs = segs;
+    j.as_host = as_host;
+    j.grad_host = grad_host;
+    j.want_loss = loss_host != nullptr;
+    j.N = N;
+    j.K = K;
+    j.H = H;
+    j.W = W;
+    j.d_img = (float *)base;
+    j.d_seg = (float *)(base + img_bytes);
+    j.d_as = (float *)(base + img_bytes + seg_bytes);
+    j.d_grad = (float *)(base + img_bytes + 2 * seg_bytes);
+    j.d_scal = (float *)(base + img_bytes + 3 * seg_bytes);  // [0]=grad_out, [1..]=loss per group, then status
+    j.d_loss = j.d_scal + 1;
+    j.d_status = (int *)(j.d_scal + 1 + ngroups);
+    j.d_ws = base + img_bytes + 3 * seg_bytes + scal_bytes;
+    j.h_gout = (float *)g_host.pin;
+    j.h_loss = j.h_gout + 1;
+    j.h_status = (int *)(j.h_loss + ngroups);
+    j.max_groups = ngroups;
+    const int hint = density_hint(j.d_ws);
+    j.dedup_hint = !lattice_is_dense(hint, pl.P);
+    j.dense_hint = lattice_is_dense(hint, pl.P);
+    *j.h_gout = grad_out;
+    cudaStream_t st = g_host.stream;
+
+    HostTrace trace;
+    int gi = 0;
+    // the captured schedule needs pinned buffers (a copy from pageable memory cannot be captured), and neither the
+    // per-stage profiler nor the trace (both record timing events between the kernels)
+    const bool graph_ok = tuning().host_graph != 0 && !g_prof.enabled && tuning().host_trace == 0 &&
+                          host_pinned(images) && host_pinned(segs) && host_pinned(as_host) && host_pinned(grad_host);
+    HostGraphs::Key key;
+    memset(&key, 0, sizeof(key));
+    HostGraphs::Item *hit = nullptr;
+    if (graph_ok) {
+        key.cfg = j.cfg;
+        key.N = N; key.K = K; key.H = H; key.W = W;
+        key.images = images; key.segs = segs; key.as_host = as_host; key.grad_host = grad_host;
+        key.buf = g_host.buf; key.pin = g_host.pin;
+        key.want_loss = j.want_loss; key.dedup = j.dedup_hint; key.dense = j.dense_hint;
+        key.groups_knob = tuning().host_groups; key.taper_knob = tuning().host_taper; key.sec0_knob = tuning().host_section0; key.grow_knob = tuning().host_grow;
+        for (auto &it : graphs.items)
+            if (it.key == key) hit = &it;
+    }
+    if (hit) {
+        hit->used = ++graphs.tick;
+        gi = hit->groups;
+        CUDA_TRY(cudaGraphLaunch(hit->exec, st));
+        std::lock_guard<std::mutex> plock(g_prof.mu);
+        g_prof.total_launches += hit->launches;
+    } else {
+        trace.begin(g_host.s_in);
+        rc = host_enqueue(g_host, j, trace, &gi);
+        if (rc) return rc;
+        trace.host_mark("enqueued");
+    }
+    density_hint_refresh(pl, j.d_ws, st);
     CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaStreamSynchronize(s_out));
+    trace.host_mark("synced");
     trace.end();
     int st_bits = 0;
     double total = 0.0;
     for (int g = 0; g < gi; g++) {
-        st_bits |= status[g];
-        total += (double)losses[g];
+        st_bits |= j.h_status[g];
+        total += (double)j.h_loss[g];
     }
     if (loss_host) *loss_host = (float)total;
+    if (graph_ok && !hit && !st_bits) {
+        // First call with these buffers: it ran eagerly (every helper object now exists and the streams are idle);
+        // capture the same schedule for the calls to come.  A failure here only means the next call is eager again.
+        if (graphs.items.size() >= 8) {   // drop the least recently used schedule
+            size_t lru = 0;
+            for (size_t i = 1; i < graphs.items.size(); i++)
+                if (graphs.items[i].used < graphs.items[lru].used) lru = i;
+            cudaGraphExecDestroy(graphs.items[lru].exec);
+            graphs.items.erase(graphs.items.begin() + lru);
+        }
+        long long launches0;
+        {
+            std::lock_guard<std::mutex> plock(g_prof.mu);
+            launches0 = g_prof.total_launches;
+        }
+        cudaGraph_t graph = nullptr;
+        int groups = 0;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            HostTrace off;
+            const int crc = host_enqueue(g_host, j, off, &groups);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (!crc && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                std::lock_guard<std::mutex> plock(g_prof.mu);
+                graphs.items.push_back({key, exec, groups, g_prof.total_launches - launches0, ++graphs.tick});
+                g_prof.total_launches = launches0;   // capturing launched nothing
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+    }
     if (st_bits)
         return fail(TCAMCRF_ERR_DEVICE_STATUS, "device status 0x%x (%s%s%s)", st_bits,
                     (st_bits & TCAMCRF_DEV_TABLE_FULL) ? "hash table full " : "",
@@ -2717,6 +2946,9 @@ int tcamcrf_set_tuning(const char *name, int value)
     else if (!strcmp(name, "HOST_GROUPS")) t.host_groups = value > 0 ? value : 0;
     else if (!strcmp(name, "HOST_SECTION0")) t.host_section0 = value > 0 ? value : 0;
     else if (!strcmp(name, "HOST_TRACE")) t.host_trace = value > 0;
+    else if (!strcmp(name, "HOST_TAPER")) t.host_taper = value;
+    else if (!strcmp(name, "HOST_GRAPH")) t.host_graph = value < 0 ? 1 : (value != 0);
+    else if (!strcmp(name, "HOST_GROW")) t.host_grow = value > 0 ? value : 0;
     else return fail(TCAMCRF_ERR_INVALID, "unknown tuning knob '%s'", name);
     return TCAMCRF_OK;
 }

@@ -263,6 +263,43 @@ def test_host_path_groups_and_chunks(torch_cuda, oracle_mod, tuning, n, groups):
     assert rel_err(grad, want_grad) < REL_TOL
 
 
+@pytest.mark.parametrize("n,k,taper", [(32, 10, None), (32, 10, "0"), (21, 7, "2"), (70, 6, None), (5, 2, "3"), (1, 10, None)])
+def test_host_path_graph_replay_and_tapered_groups(torch_cuda, oracle_mod, tuning, n, k, taper):
+    """Host-pointer path with PINNED buffers: the first call runs the three-stream schedule eagerly and captures it,
+    later calls replay the CUDA graph (one launch per call).  Eager call, two replays with new data in the same
+    buffers, and the graph switched off must all match the oracle; the value-stage groups taper towards the end of the
+    batch (TCAMCRF_HOST_TAPER) or are equal (0).  New buffers take a new schedule."""
+    import ctypes
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import _lib
+    tuning("HOST_TAPER", taper)
+    lib = _lib.load()
+    h, w = 20, 24
+    cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0)
+    bufs = [(torch.empty(n, 3, h, w).pin_memory(), torch.empty(n, k, h, w).pin_memory(),
+             torch.empty(1).pin_memory(), torch.empty(n, k, h, w).pin_memory()) for _ in range(2)]
+    launches = []
+    for call in range(5):
+        img_h, seg_h, loss_h, grad_h = bufs[0] if call != 3 else bufs[1]
+        if call == 4:
+            tuning("HOST_GRAPH", 0)
+        img = synth.make_images(n, h, w, "noise" if call % 2 == 0 else "natural", seed=50 + call)
+        seg = synth.make_segs(n, k, h, w, seed=50 + call)
+        img_h.copy_(torch.from_numpy(img))
+        seg_h.copy_(torch.from_numpy(seg))
+        grad_h.zero_()
+        l0 = lib.tcamcrf_launch_count()
+        _lib.check(lib.tcamcrf_loss_fwd_bwd_host(ctypes.byref(cfg), img_h.data_ptr(), seg_h.data_ptr(),
+                                                 loss_h.data_ptr(), grad_h.data_ptr(), n, k, h, w, 0.25), "fwd_bwd_host")
+        launches.append(lib.tcamcrf_launch_count() - l0)
+        want_loss, want_grad, _ = oracle_mod.densecrf_loss_fwd_bwd(img, seg, 15.0, 100.0, 0.25,
+                                                                   oracle_mod.port_bilateralfilter_batch)
+        assert abs(float(loss_h[0]) - float(want_loss)) < REL_TOL * abs(float(want_loss)), f"call {call}"
+        assert rel_err(grad_h.numpy(), want_grad) < REL_TOL, f"call {call}"
+    # a replay accounts for as many kernels as the eager call it was captured from
+    assert launches[1] == launches[0] and launches[2] == launches[0] and launches[0] > 0, launches
+
+
 @pytest.mark.parametrize("n,sections", [(32, None), (5, None), (70, None), (9, "1"), (13, "64"), (1, None)])
 def test_host_frames_path(torch_cuda, oracle_mod, tuning, n, sections):
     """Frames left on the CPU in pinned memory (what the reference's trainer passes) take

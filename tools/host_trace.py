@@ -11,5 +11,9 @@ cfg=_lib.make_config(_lib.FEAT_XY_RGB,3,15.0,100.0)
 def step():
     _lib.check(lib.tcamcrf_loss_fwd_bwd_host(ctypes.byref(cfg), img.data_ptr(), seg.data_ptr(), loss.data_ptr(), grad.data_ptr(), N,K,H,W, 2e-9),"x")
 for _ in range(5): step()
-os.environ["TCAMCRF_HOST_TRACE"]="1"
+_lib.set_tuning("HOST_TRACE", 1)
 t0=time.perf_counter(); step(); print("wall ms", (time.perf_counter()-t0)*1e3)
+_lib.set_tuning("HOST_TRACE", 0)
+t0=time.perf_counter()
+for _ in range(20): step()
+print("mean wall ms over 20", (time.perf_counter()-t0)*1e3/20)
