@@ -268,6 +268,26 @@ int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const
 int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
                      int64_t *out_dev, void *cuda_stream);
 
+/* The whole seeding step of a batch in ONE launch (a thread-block cluster of 8 blocks per sample): temporal max
+ * (cam_max_dev [B,H*W] out), candidate counts, fg and bg selection, label map.  Replaces the per-sample loop of
+ * TCAMSeeder.forward (dlib/cams/tcam_seeding.py:232-254) with _OneSample / _SFG / _SBG (:433-592) inside it:
+ *   - candidate counts like the reference: none for a flat CAM (cam.min() == cam.max(), :465); fg: int(max_p * roi.sum())
+ *     as a float32 product (:510,519), or n_fg_fixed = int(max_p*H*W) without a roi (:515); bg: n_bg = int(min_p*H*W)
+ *     (:567).  n_cand_dev [B,2], when given, overrides them (a caller that sized its draws from its own counts);
+ *   - candidates = the n largest (fg, on cam*roi + 1e-8) / smallest (bg, on cam + 1e-8) values, ties to the lowest
+ *     pixel index (stable sort); selected = top-k of p / q, p = value (weighted_fg) or 1;
+ *   - q: the caller's Exp(1) draws in row-major candidate order (q_dev + q_offset_dev [B,2]: bit-identical to
+ *     tcam_seed_select, i.e. to the reference's multinomial given the same stream), or, with q_dev == NULL, drawn in
+ *     the kernel by Philox4x32-10 keyed with the two words at rng_dev (fresh per call, e.g. from torch's generator);
+ *   - labels_dev [B,H,W] int64 (or NULL): flat ksz x ksz dilation of the seeds, conflicts -> ignore (:239-254).
+ * sel_dev [B,2,kmax] pixel indices (-1 = unused).  tcam_seed_fused_supported: the slice of a frame (H*W/8 pixels,
+ * 8 bytes each) must fit the shared memory of an SM and kmax <= 32; otherwise use tcam_seed_select + tcam_seed_labels. */
+int tcam_seed_fused_supported(int HW, int kmax);
+int tcam_seed_fused(const float *cams_dev, int T, const int64_t *roi_dev, const float *q_dev, const int *q_offset_dev,
+                    const int *n_cand_dev, const unsigned int *rng_dev, float max_p, int n_fg_fixed, int n_bg, int k_fg,
+                    int k_bg, int weighted_fg, int B, int H, int W, int ksz, long long ignore_idx, float *cam_max_dev,
+                    int *sel_dev, int kmax, int64_t *labels_dev, void *cuda_stream);
+
 /* ROI of every CAM of a batch by Otsu's threshold: roi = (cam*255 >= otsu(floor(cam*255))), 1/0 as int64, the
  * 'roi_all' branch of GetRoiSingleCam (dlib/cams/tcam_seeding.py:316-345,419-430; scikit-image threshold_otsu
  * on a 256-bin np.histogram, float32 edges).  cams_dev [B,HW] float32, roi_dev [B,HW], thresh_dev [B] or NULL. */

@@ -16,6 +16,7 @@
 // the selection is bit-exact given the same draws.
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace tcamcrf {
@@ -412,6 +413,477 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_smem_kernel(const Se
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The whole seeding step of a batch in ONE launch, at GPU width: a thread-block CLUSTER of 8 blocks per sample.
+//
+// seed_select[_smem]_kernel run one block per (sample, fg|bg): 64 blocks on 148 SMs, the temporal max taken by both
+// blocks, four serial 256-bin scans by one thread, candidate counts from five torch reductions, 2*H*W exponential draws
+// per sample made by torch (12.8 MB per step) to use a few of them, and a second launch for the label map.  Here:
+//   * block r of the cluster owns pixels [r*slice, (r+1)*slice) of the sample: ONE pass over the T planes (float4)
+//     gives the temporal max (written out), min / max / roi count for the candidate counts (tcam_seeding.py:465,510,519,
+//     567) and the fg and bg selection keys, kept in shared memory (2 x 4 bytes per pixel of the slice);
+//   * 4-pass radix select for both sides at once: per-block 256-bin histograms in shared memory, summed across the
+//     cluster by reading the other blocks' histograms through distributed shared memory (one cluster barrier per pass,
+//     histograms double-buffered), bin scan by one warp per side;
+//   * ties at the threshold go to the lowest pixel indices (stable sort), row-major candidate ranks come from block
+//     scans + a cluster-wide exclusive prefix -- needed only when the draws are an INPUT (rng_parity: bit-identical to
+//     the reference's stream); otherwise the Exp(1) draw of a candidate comes from Philox4x32-10 keyed by two words
+//     torch's CUDA generator produced for this call and counted by (sample, side, pixel): only candidates draw;
+//   * top-k by score p/q: k rounds of block arg-max + cluster all-gather; then every block writes the label map of its
+//     slice (kornia's flat ksz x ksz dilation of the fg / bg seeds, conflicts -> ignore, tcam_seeding.py:239-254).
+// Results are bit-identical to seed_select_kernel + seed_labels_kernel when the draws are given.
+namespace cg = cooperative_groups;
+
+constexpr int kSeedCluster = 8;          // portable cluster size
+constexpr int kSeedFusedThreads = 512;
+constexpr int kSeedFusedMaxK = 32;       // seeds per side this kernel handles (larger k: the two-kernel path)
+
+struct SeedFusedParams {
+    const float *cams;          // [B][T][HW]
+    const long long *roi;       // [B][HW] or null
+    const float *q;             // exponential draws in candidate order, or null -> Philox
+    const int *q_offset;        // [B][2] (with q)
+    const int *n_cand;          // [B][2] candidate counts computed by the caller, or null -> computed here
+    const unsigned int *rng;    // [2] Philox key words (with q == null)
+    float *cam_max;             // [B][HW]
+    int *sel;                   // [B][2][kmax]
+    long long *labels;          // [B][HW] or null
+    int T, HW, H, W, kmax, k_fg, k_bg, weighted_fg;
+    float max_p;                // float32(max_p): n_fg = int(max_p * roi.sum()) as a float32 product
+    int n_fg_fixed;             // n_fg without a roi: int(max_p * H * W)
+    int n_bg;                   // int(min_p * H * W)
+    int ksz;
+    long long ignore_idx;
+    int slice;                  // pixels per block of the cluster (multiple of 4)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Exp(1) draw of (sample, side, pixel): -log(u), u uniform in (0, 1)
+__device__ __forceinline__ float seed_exp_draw(uint2 key, int b, int side, int pixel)
+{
+    const uint4 r = philox4x32_10(make_uint4((unsigned int)pixel, (unsigned int)(b * 2 + side), 0x5eedu, 0u), key);
+    const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return -__logf(u);
+}
+
+__device__ __forceinline__ float nanmax(float m, float v)   // torch.maximum: NaN if either is NaN
+{
+    return (m != m) ? m : ((v != v) ? v : (v > m ? v : m));
+}
+
+// block-wide exclusive scan for kSeedFusedThreads threads (same contract as block_exclusive_scan)
+__device__ __forceinline__ int fused_exclusive_scan(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kSeedFusedThreads / 32 ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(kSeedFusedThreads) seed_fused_kernel(const SeedFusedParams p)
+{
+    extern __shared__ unsigned int s_key[];           // [2][slice]: keys, later scores (fg first)
+    __shared__ int s_hist[2][2][256];                 // [buffer][side][bin]
+    __shared__ int s_tot[2][256];
+    __shared__ int s_gi[2][kSeedCluster][4];          // small all-gathers across the cluster, double-buffered
+    __shared__ float s_gf[2][kSeedCluster][2];
+    __shared__ int s_warp[33];
+    __shared__ float s_rf[2][kSeedFusedThreads / 32];
+    __shared__ int s_ri[2][kSeedFusedThreads / 32];
+    __shared__ unsigned int s_prefix[2];
+    __shared__ int s_need[2];
+    __shared__ int s_sel[2][kSeedFusedMaxK];
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HW = p.HW, slice = p.slice;
+    const int lo = min(rank * slice, HW), hi = min(lo + slice, HW);
+    const int cnt = hi - lo;
+    const float *cam0 = p.cams + (size_t)b * p.T * HW;
+    float *cmax = p.cam_max + (size_t)b * HW;
+    const long long *roi = p.roi ? p.roi + (size_t)b * HW : nullptr;
+    unsigned int *key_fg = s_key, *key_bg = s_key + slice;
+    int gbuf = 0;   // which gather buffer the next all-gather uses
+
+    // every block of the cluster writes `vals` into slot [rank] of EVERY block's gather buffer
+    auto gather_put_i = [&](int buf, int v0, int v1, int v2, int v3) {
+        if (tid < kSeedCluster) {
+            int *dst = cluster.map_shared_rank(&s_gi[buf][rank][0], tid);
+            dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
+        }
+    };
+
+    // ---- pass 0: temporal max, keys, statistics of the slice
+    float mn = INFINITY, mx = -INFINITY;
+    int has_nan = 0, roi_sum = 0;
+    auto take = [&](int i, float m) {   // i: index within the slice
+        has_nan |= (m != m);
+        mn = fminf(mn, m);
+        mx = fmaxf(mx, m);
+        float vfg = m;
+        if (roi) {
+            const long long r = __ldg(roi + lo + i);
+            roi_sum += (int)r;
+            vfg = __fmul_rn(m, (float)r);
+        }
+        key_fg[i] = ~float_order_key(__fadd_rn(vfg, 1e-8f));   // the n SMALLEST keys are the candidates
+        key_bg[i] = float_order_key(__fadd_rn(m, 1e-8f));
+    };
+    if ((HW & 3) == 0) {   // slice and HW are multiples of 4: whole float4s
+        for (int i4 = tid; i4 < cnt / 4; i4 += kSeedFusedThreads) {
+            float4 m = __ldg(reinterpret_cast<const float4 *>(cam0 + lo) + i4);
+            for (int t = 1; t < p.T; t++) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(cam0 + (size_t)t * HW + lo) + i4);
+                m.x = nanmax(m.x, v.x);
+                m.y = nanmax(m.y, v.y);
+                m.z = nanmax(m.z, v.z);
+                m.w = nanmax(m.w, v.w);
+            }
+            reinterpret_cast<float4 *>(cmax + lo)[i4] = m;
+            take(4 * i4 + 0, m.x);
+            take(4 * i4 + 1, m.y);
+            take(4 * i4 + 2, m.z);
+            take(4 * i4 + 3, m.w);
+        }
+    } else {
+        for (int i = tid; i < cnt; i += kSeedFusedThreads) {
+            float m = __ldg(cam0 + lo + i);
+            for (int t = 1; t < p.T; t++) m = nanmax(m, __ldg(cam0 + (size_t)t * HW + lo + i));
+            cmax[lo + i] = m;
+            take(i, m);
+        }
+    }
+    for (int i = tid; i < 2 * kSeedFusedMaxK; i += kSeedFusedThreads) (&s_sel[0][0])[i] = -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
+        roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, o);
+    }
+    if (lane == 0) {
+        s_rf[0][warp] = mn;
+        s_rf[1][warp] = mx;
+        s_ri[0][warp] = has_nan;
+        s_ri[1][warp] = roi_sum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kSeedFusedThreads / 32; w++) {
+            mn = fminf(mn, s_rf[0][w]);
+            mx = fmaxf(mx, s_rf[1][w]);
+            has_nan |= s_ri[0][w];
+            roi_sum += s_ri[1][w];
+        }
+        s_rf[0][0] = mn;
+        s_rf[1][0] = mx;
+        s_ri[0][0] = has_nan;
+        s_ri[1][0] = roi_sum;
+    }
+    __syncthreads();
+    gather_put_i(gbuf, __float_as_int(s_rf[0][0]), __float_as_int(s_rf[1][0]), s_ri[0][0], s_ri[1][0]);
+    cluster.sync();
+    int n[2], k[2];
+    {
+        float gmn = INFINITY, gmx = -INFINITY;
+        int gnan = 0, gsum = 0;
+        for (int r = 0; r < kSeedCluster; r++) {
+            gmn = fminf(gmn, __int_as_float(s_gi[gbuf][r][0]));
+            gmx = fmaxf(gmx, __int_as_float(s_gi[gbuf][r][1]));
+            gnan |= s_gi[gbuf][r][2];
+            gsum += s_gi[gbuf][r][3];
+        }
+        // flat CAM: no seeds at all (cam.min() == cam.max(), tcam_seeding.py:465; NaN compares unequal)
+        const bool alive = gnan || gmn != gmx;
+        n[0] = roi ? (int)__fmul_rn(p.max_p, (float)gsum) : p.n_fg_fixed;   // tcam_seeding.py:510,515,519
+        n[1] = p.n_bg;                                                       // tcam_seeding.py:567
+        if (p.k_fg <= 0 || !alive) n[0] = 0;
+        if (p.k_bg <= 0 || !alive) n[1] = 0;
+        if (p.n_cand) {   // the caller's counts (sized its draws with them)
+            n[0] = p.n_cand[b * 2];
+            n[1] = p.n_cand[b * 2 + 1];
+        }
+        n[0] = min(n[0], HW);
+        n[1] = min(n[1], HW);
+        k[0] = min(min(p.k_fg, n[0]), p.kmax);
+        k[1] = min(min(p.k_bg, n[1]), p.kmax);
+    }
+    gbuf ^= 1;
+    const bool on[2] = {n[0] > 0 && k[0] > 0, n[1] > 0 && k[1] > 0};
+
+    if (on[0] || on[1]) {
+        // ---- radix select, 8 bits at a time from the top, both sides at once
+        if (tid < 2) {
+            s_prefix[tid] = 0;
+            s_need[tid] = n[tid];
+        }
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            const int hb = pass & 1;
+            for (int i = tid; i < 512; i += kSeedFusedThreads) (&s_hist[hb][0][0])[i] = 0;
+            __syncthreads();
+            const unsigned int himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (!on[side]) continue;
+                const unsigned int prefix = s_prefix[side];
+                const unsigned int *keys = side ? key_bg : key_fg;
+                for (int i = tid; i < cnt; i += kSeedFusedThreads) {
+                    const unsigned int key = keys[i];
+                    if ((key & himask) == prefix) atomicAdd(&s_hist[hb][side][(key >> shift) & 255u], 1);
+                }
+            }
+            cluster.sync();   // every block's histogram of this pass is complete
+            {   // thread (side, bin): the bin summed over the cluster
+                const int side = tid >> 8, bin = tid & 255;
+                int sum = 0;
+                for (int r = 0; r < kSeedCluster; r++) sum += *cluster.map_shared_rank(&s_hist[hb][side][bin], r);
+                s_tot[side][bin] = sum;
+            }
+            __syncthreads();
+            if (warp < 2 && on[warp]) {   // one warp per side: which bin holds the need-th key
+                const int side = warp;
+                int c[8], mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    c[j] = s_tot[side][lane * 8 + j];
+                    mine += c[j];
+                }
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int need = s_need[side];
+                const int excl = incl - mine;
+                const unsigned int holds = __ballot_sync(0xffffffffu, excl < need && need <= incl);
+                __syncwarp();
+                if (holds && lane == __ffs(holds) - 1) {
+                    int run = excl, bin = lane * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (run + c[j] >= need) break;
+                        run += c[j];
+                        bin++;
+                    }
+                    s_prefix[side] |= (unsigned int)bin << shift;
+                    s_need[side] = need - run;
+                }
+            }
+            __syncthreads();
+        }
+        // keys < kth are candidates; of the keys == kth the first `need` by pixel index
+        // ---- row-major ranks: thread t owns pixels [t*chunk, (t+1)*chunk) of the slice
+        const int chunk = (slice + kSeedFusedThreads - 1) / kSeedFusedThreads;
+        const int clo = min(tid * chunk, cnt), chi = min(clo + chunk, cnt);
+        int tie_rank[2] = {0, 0}, cand_rank[2] = {0, 0};
+        {
+            int my_ties[2] = {0, 0}, tot[2];
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (on[side]) {
+                    const unsigned int *keys = side ? key_bg : key_fg;
+                    const unsigned int kth = s_prefix[side];
+                    for (int i = clo; i < chi; i++) my_ties[side] += keys[i] == kth;
+                }
+                tie_rank[side] = fused_exclusive_scan(my_ties[side], s_warp, tot[side]);
+            }
+            gather_put_i(gbuf, tot[0], tot[1], 0, 0);
+            cluster.sync();
+            for (int r = 0; r < rank; r++) {
+                tie_rank[0] += s_gi[gbuf][r][0];
+                tie_rank[1] += s_gi[gbuf][r][1];
+            }
+            gbuf ^= 1;
+        }
+        if (p.q) {   // the draws are an input, in row-major candidate order: global candidate ranks
+            int my_c[2] = {0, 0}, tot[2];
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (on[side]) {
+                    const unsigned int *keys = side ? key_bg : key_fg;
+                    const unsigned int kth = s_prefix[side];
+                    const int need = s_need[side];
+                    int tr = tie_rank[side];
+                    for (int i = clo; i < chi; i++) {
+                        const unsigned int key = keys[i];
+                        if (key < kth) my_c[side]++;
+                        else if (key == kth) my_c[side] += (tr++ < need);
+                    }
+                }
+                cand_rank[side] = fused_exclusive_scan(my_c[side], s_warp, tot[side]);
+            }
+            gather_put_i(gbuf, tot[0], tot[1], 0, 0);
+            cluster.sync();
+            for (int r = 0; r < rank; r++) {
+                cand_rank[0] += s_gi[gbuf][r][0];
+                cand_rank[1] += s_gi[gbuf][r][1];
+            }
+            gbuf ^= 1;
+        }
+        // ---- scores replace the keys: p / q for candidates (torch.multinomial without replacement), -inf otherwise
+        uint2 rkey = make_uint2(0u, 0u);
+        if (!p.q) rkey = make_uint2(__ldg(p.rng), __ldg(p.rng + 1));
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            if (!on[side]) continue;
+            unsigned int *keys = side ? key_bg : key_fg;
+            const unsigned int kth = s_prefix[side];
+            const int need = s_need[side];
+            const bool weighted = side == 0 && p.weighted_fg;
+            const float *q = p.q ? p.q + p.q_offset[b * 2 + side] : nullptr;
+            int tr = tie_rank[side], cr = cand_rank[side];
+            for (int i = clo; i < chi; i++) {
+                const unsigned int key = keys[i];
+                bool is_cand = key < kth;
+                if (key == kth) is_cand = tr++ < need;
+                float sc = -INFINITY;
+                if (is_cand) {
+                    const float val = float_from_order_key(side ? key : ~key);
+                    const float draw = q ? __ldg(q + cr++) : seed_exp_draw(rkey, b, side, lo + i);
+                    sc = __fdiv_rn(weighted ? val : 1.0f, draw);
+                }
+                keys[i] = __float_as_uint(sc);
+            }
+        }
+        __syncthreads();
+        // ---- top-k: k rounds of arg-max over the sample (lowest index wins ties), the winner retires with -inf
+        const int rounds = max(on[0] ? k[0] : 0, on[1] ? k[1] : 0);
+        for (int round = 0; round < rounds; round++) {
+            float bv[2] = {-INFINITY, -INFINITY};
+            int bi[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (!(on[side] && round < k[side])) continue;
+                const unsigned int *keys = side ? key_bg : key_fg;
+                for (int i = tid; i < cnt; i += kSeedFusedThreads) {
+                    const float sc = __uint_as_float(keys[i]);
+                    if (sc > bv[side] || (sc == bv[side] && lo + i < bi[side] && sc != -INFINITY)) {
+                        bv[side] = sc;
+                        bi[side] = lo + i;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv[side], o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi[side], o);
+                    if (ov > bv[side] || (ov == bv[side] && oi < bi[side])) {
+                        bv[side] = ov;
+                        bi[side] = oi;
+                    }
+                }
+                if (lane == 0) {
+                    s_rf[side][warp] = bv[side];
+                    s_ri[side][warp] = bi[side];
+                }
+            }
+            __syncthreads();
+            if (tid < 2) {
+                const int side = tid;
+                float v = -INFINITY;
+                int ix = 0x7fffffff;
+                if (on[side] && round < k[side])
+                    for (int w = 0; w < kSeedFusedThreads / 32; w++) {
+                        const float ov = s_rf[side][w];
+                        const int oi = s_ri[side][w];
+                        if (ov > v || (ov == v && oi < ix)) {
+                            v = ov;
+                            ix = oi;
+                        }
+                    }
+                for (int r = 0; r < kSeedCluster; r++) {   // all-gather of (value, index) of this block
+                    *cluster.map_shared_rank(&s_gf[gbuf][rank][side], r) = v;
+                    *cluster.map_shared_rank(&s_gi[gbuf][rank][side], r) = ix;
+                }
+            }
+            cluster.sync();
+            if (tid < 2) {
+                const int side = tid;
+                if (on[side] && round < k[side]) {
+                    float v = -INFINITY;
+                    int ix = 0x7fffffff;
+                    for (int r = 0; r < kSeedCluster; r++) {
+                        const float ov = s_gf[gbuf][r][side];
+                        const int oi = s_gi[gbuf][r][side];
+                        if (ov > v || (ov == v && oi < ix)) {
+                            v = ov;
+                            ix = oi;
+                        }
+                    }
+                    if (v > -INFINITY && ix < HW) {
+                        s_sel[side][round] = ix;
+                        if (ix >= lo && ix < hi) (side ? key_bg : key_fg)[ix - lo] = __float_as_uint(-INFINITY);
+                    }
+                }
+            }
+            gbuf ^= 1;
+            __syncthreads();
+        }
+    }
+    // ---- outputs: the selected pixels, and the label map of this block's slice
+    if (rank == 0)
+        for (int i = tid; i < 2 * p.kmax; i += kSeedFusedThreads) {
+            const int side = i / p.kmax, j = i - side * p.kmax;
+            p.sel[((size_t)b * 2 + side) * p.kmax + j] = j < kSeedFusedMaxK ? s_sel[side][j] : -1;
+        }
+    if (p.labels) {
+        // kornia 0.6.4 dilation with a flat ksz x ksz kernel (see seed_labels_kernel)
+        const int origin = p.ksz / 2, back = p.ksz - 1 - origin;
+        long long *out = p.labels + (size_t)b * HW;
+        const int kk = min(p.kmax, kSeedFusedMaxK);
+        for (int i = lo + tid; i < hi; i += kSeedFusedThreads) {
+            const int y = i / p.W, x = i - y * p.W;
+            bool near[2] = {false, false};
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+                for (int j = 0; j < kk; j++) {
+                    const int sp = s_sel[c][j];
+                    if (sp < 0) break;
+                    const int sy = sp / p.W, sx = sp - sy * p.W;
+                    if (y >= sy - back && y <= sy + origin && x >= sx - back && x <= sx + origin) near[c] = true;
+                }
+            long long label = p.ignore_idx;
+            if (near[0] != near[1]) label = near[0] ? 1 : 0;   // claimed by both -> neither (tcam_seeding.py:247-250)
+            out[i] = label;
+        }
     }
 }
 

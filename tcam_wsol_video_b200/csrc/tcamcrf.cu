@@ -3039,6 +3039,95 @@ int tcam_seed_select(const float *cams_dev, int T, const int64_t *roi_dev, const
     return TCAMCRF_OK;
 }
 
+// Largest dynamic shared memory seed_fused_kernel may use on this device (0: the opt-in was refused).
+static int seed_fused_smem_limit()
+{
+    static int limit = -1;
+    if (limit < 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        int stat = 12 * 1024;
+        if (cudaFuncGetAttributes(&fa, seed_fused_kernel) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+        optin -= stat + 1024;
+        if (optin > 0 && cudaFuncSetAttribute(seed_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) ==
+                             cudaSuccess)
+            limit = optin;
+        else {
+            cudaGetLastError();
+            limit = 0;
+        }
+    }
+    return limit;
+}
+
+static int seed_fused_slice(int HW) { return ((HW + kSeedCluster - 1) / kSeedCluster + 3) / 4 * 4; }
+
+int tcam_seed_fused_supported(int HW, int kmax)
+{
+    if (HW < 1 || kmax < 1 || kmax > kSeedFusedMaxK) return 0;
+    return (size_t)seed_fused_slice(HW) * 2 * sizeof(unsigned int) <= (size_t)seed_fused_smem_limit() ? 1 : 0;
+}
+
+int tcam_seed_fused(const float *cams_dev, int T, const int64_t *roi_dev, const float *q_dev, const int *q_offset_dev,
+                    const int *n_cand_dev, const unsigned int *rng_dev, float max_p, int n_fg_fixed, int n_bg, int k_fg,
+                    int k_bg, int weighted_fg, int B, int H, int W, int ksz, long long ignore_idx, float *cam_max_dev,
+                    int *sel_dev, int kmax, int64_t *labels_dev, void *cuda_stream)
+{
+    if (!cams_dev || !cam_max_dev || !sel_dev) return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || T < 1 || H < 1 || W < 1 || kmax < 1 || k_fg < 0 || k_bg < 0 || ksz < 1)
+        return fail(TCAMCRF_ERR_INVALID, "B,T,H,W,kmax,ksz must be positive and k_fg,k_bg non-negative");
+    if ((long long)H * W > (1ll << 26)) return fail(TCAMCRF_ERR_INVALID, "image too large");
+    if (q_dev ? (!q_offset_dev || !n_cand_dev) : !rng_dev)
+        return fail(TCAMCRF_ERR_INVALID, "draws need q_offset and n_cand; without draws the Philox key words are needed");
+    const int HW = H * W;
+    if (!tcam_seed_fused_supported(HW, kmax))
+        return fail(TCAMCRF_ERR_INVALID, "tcam_seed_fused: frame too large for shared memory or kmax > %d "
+                    "(use tcam_seed_select + tcam_seed_labels)", kSeedFusedMaxK);
+    if (B > 65535) return fail(TCAMCRF_ERR_INVALID, "batch too large");
+    SeedFusedParams sp;
+    sp.cams = cams_dev;
+    sp.roi = reinterpret_cast<const long long *>(roi_dev);
+    sp.q = q_dev;
+    sp.q_offset = q_offset_dev;
+    sp.n_cand = n_cand_dev;
+    sp.rng = rng_dev;
+    sp.cam_max = cam_max_dev;
+    sp.sel = sel_dev;
+    sp.labels = reinterpret_cast<long long *>(labels_dev);
+    sp.T = T;
+    sp.HW = HW;
+    sp.H = H;
+    sp.W = W;
+    sp.kmax = kmax;
+    sp.k_fg = k_fg;
+    sp.k_bg = k_bg;
+    sp.weighted_fg = weighted_fg;
+    sp.max_p = max_p;
+    sp.n_fg_fixed = n_fg_fixed;
+    sp.n_bg = n_bg;
+    sp.ksz = ksz;
+    sp.ignore_idx = ignore_idx;
+    sp.slice = seed_fused_slice(HW);
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(kSeedCluster, B);
+    lc.blockDim = dim3(kSeedFusedThreads);
+    lc.dynamicSmemBytes = (size_t)sp.slice * 2 * sizeof(unsigned int);
+    lc.stream = (cudaStream_t)cuda_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSeedCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, seed_fused_kernel, sp));
+    return TCAMCRF_OK;
+}
+
 int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
                      int64_t *out_dev, void *cuda_stream)
 {

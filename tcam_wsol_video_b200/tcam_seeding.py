@@ -4,14 +4,18 @@ Same constructor arguments, same ``forward(x, roi=None)`` contract (``x`` CAMs `
 ``roi`` long ``[B,1,H,W]``; returns long ``[B,H,W]`` in {ignore, 0 bg, 1 fg}), ``set_seed_tech``,
 ``use_all_roi`` and ``extra_repr``.  The reference loops over the samples in Python and, per sample, runs two
 full stable sorts, ``nonzero``, ``multinomial`` and several host syncs (tcam_seeding.py:232-237,453-592);
-here the whole batch is two kernel launches (``tcam_seed_select`` + ``tcam_seed_labels``, csrc/seed.cuh) and
-ONE host sync (to size the random draws exactly like the reference does).
+here the whole batch is ONE kernel launch (``tcam_seed_fused``, csrc/seed.cuh: a thread-block cluster per sample does
+the temporal max, the candidate counts, both selections and the label map; frames too large for an SM's shared memory
+take ``tcam_seed_select`` + ``tcam_seed_labels``) and, with ``rng_parity=True``, ONE host sync (to size the random
+draws exactly like the reference does).
 
 Random draws.  ``torch.multinomial(probs, k, replacement=False)`` is ``topk(probs / q)`` with
 ``q = empty_like(probs).exponential_(1)``.  With ``rng_parity=True`` (default) the draws are taken from the
 current torch CUDA generator with the same sizes and in the same order as the reference's calls
 (sample 0 fg, sample 0 bg, sample 1 fg, ...), so for the same seed the seeds are bit-identical to the
-reference's.  ``rng_parity=False`` draws everything in one call (same distribution, different stream).
+reference's.  ``rng_parity=False`` makes the Exp(1) draws inside the kernel (Philox4x32-10, keyed by two words taken
+from torch's CUDA generator per call: ``torch.manual_seed`` still makes runs repeatable; same distribution, different
+stream), only for the candidates: no host sync, no draw tensor, capturable in a CUDA graph.
 
 ``use_roi=True`` with ``roi=None``: the reference computes the ROI on the CPU with scikit-image's Otsu, one
 sample at a time (tcam_seeding.py:476-479); here ``roi_method='roi_all'`` runs as one kernel for the batch
@@ -182,33 +186,52 @@ class TCAMSeeder(nn.Module):
 
     def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts):
         """cams [B,T,H,W] float32 CUDA -> (labels [B,H,W] long, cam_max [B,H,W]).  counts: numpy [B,2] (draws sized and
-        ordered like the reference's multinomial calls) or an int32 CUDA tensor [B,2] (no host round trip: every
-        (sample, fg|bg) gets a fixed slot of H*W draws)."""
+        ordered like the reference's multinomial calls) or None (no host round trip: counts and draws are made by the
+        kernel)."""
         lib = _lib.load()
         b, t, h, w = cams.shape
         device = cams.device
         kmax = max(self.max_, self.min_, 1)
-        if torch.is_tensor(counts):
-            q = torch.empty(b * 2 * h * w, dtype=torch.float32, device=device).exponential_(1)
-            q_off = torch.arange(2 * b, dtype=torch.int32, device=device) * (h * w)
-            n_cand = counts.reshape(-1)
+        fused = bool(lib.tcam_seed_fused_supported(h * w, kmax))
+        n_fg_fixed = int(self.max_p * (h * w)) if self.max_ > 0 else 0       # tcam_seeding.py:515,519
+        n_bg = int(self.min_p * h * w) if self.min_ > 0 else 0                # tcam_seeding.py:567
+        rng = q = q_off = n_cand = None
+        if counts is None and fused:
+            # two words from torch's CUDA generator key the in-kernel Philox stream of this call
+            rng = torch.randint(0, 2 ** 31 - 1, (2,), dtype=torch.int32, device=device)
         else:
-            q, offsets = self._draws(counts, device)
-            meta = torch.from_numpy(np.concatenate([offsets.reshape(-1), counts.reshape(-1)]).astype(np.int32)).to(device)
-            q_off, n_cand = meta[: 2 * b], meta[2 * b:]
+            if counts is None:
+                counts_t = self._candidate_counts_device(cams.amax(dim=1, keepdim=True) if t > 1 else cams, roi)
+                q = torch.empty(b * 2 * h * w, dtype=torch.float32, device=device).exponential_(1)
+                q_off = torch.arange(2 * b, dtype=torch.int32, device=device) * (h * w)
+                n_cand = counts_t.reshape(-1)
+            else:
+                q, offsets = self._draws(counts, device)
+                meta = torch.from_numpy(np.concatenate([offsets.reshape(-1), counts.reshape(-1)]).astype(np.int32)).to(device)
+                q_off, n_cand = meta[: 2 * b], meta[2 * b:]
         cam_max = torch.empty((b, h, w), dtype=torch.float32, device=device)
-        scratch = torch.empty((b, 2, h * w), dtype=torch.float32, device=device)
         sel = torch.empty((b, 2, kmax), dtype=torch.int32, device=device)
         out = torch.empty((b, h, w), dtype=torch.long, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
-            _lib.check(lib.tcam_seed_select(cams.data_ptr(), t, roi.data_ptr() if roi is not None else None,
-                                            q.data_ptr(), q_off.data_ptr(), n_cand.data_ptr(), self.max_, self.min_,
-                                            1 if self.seed_tech == SEED_WEIGHTED else 0, b, h * w,
-                                            cam_max.data_ptr(), scratch.data_ptr(), sel.data_ptr(), kmax, stream),
-                       'tcam_seed_select')
-            _lib.check(lib.tcam_seed_labels(sel.data_ptr(), kmax, b, h, w, self.ksz, int(self.ignore_idx),
-                                            out.data_ptr(), stream), 'tcam_seed_labels')
+            if fused:
+                _lib.check(lib.tcam_seed_fused(
+                    cams.data_ptr(), t, roi.data_ptr() if roi is not None else None,
+                    q.data_ptr() if q is not None else None, q_off.data_ptr() if q is not None else None,
+                    n_cand.data_ptr() if n_cand is not None else None, rng.data_ptr() if rng is not None else None,
+                    float(np.float32(self.max_p)), n_fg_fixed, n_bg, self.max_, self.min_,
+                    1 if self.seed_tech == SEED_WEIGHTED else 0, b, h, w, self.ksz, int(self.ignore_idx),
+                    cam_max.data_ptr(), sel.data_ptr(), kmax, out.data_ptr(), stream), 'tcam_seed_fused')
+            else:
+                scratch = torch.empty((b, 2, h * w), dtype=torch.float32, device=device)
+                _lib.check(lib.tcam_seed_select(cams.data_ptr(), t, roi.data_ptr() if roi is not None else None,
+                                                q.data_ptr(), q_off.data_ptr(), n_cand.data_ptr(), self.max_, self.min_,
+                                                1 if self.seed_tech == SEED_WEIGHTED else 0, b, h * w,
+                                                cam_max.data_ptr(), scratch.data_ptr(), sel.data_ptr(), kmax, stream),
+                           'tcam_seed_select')
+                _lib.check(lib.tcam_seed_labels(sel.data_ptr(), kmax, b, h, w, self.ksz, int(self.ignore_idx),
+                                                out.data_ptr(), stream), 'tcam_seed_labels')
+        self._last_sel = sel
         return out, cam_max
 
     def _prep(self, x: torch.Tensor, roi: Optional[torch.Tensor]):
@@ -240,7 +263,7 @@ class TCAMSeeder(nn.Module):
         x, _roi = self._prep(x, roi)
         b, d, h, w = x.shape
         assert d == 1, d  # todo multilabel.
-        counts = self._candidate_counts(x, _roi)[0] if self.rng_parity else self._candidate_counts_device(x, _roi)
+        counts = self._candidate_counts(x, _roi)[0] if self.rng_parity else None
         out, _ = self._select(x, _roi, counts)
         return out.detach()
 
@@ -249,11 +272,22 @@ class TCAMSeeder(nn.Module):
         resolution).  Returns (seeds [B,H,W] long, cam_max [B,H,W]); identical to
         ``forward(cams.max-chain over T)`` (dlib/datasets/wsol_loader.py:591-600 followed by TCAMSeeder)."""
         assert cams.ndim == 4
-        x_max = ops.temporal_cam_max(cams.detach().float().contiguous()).unsqueeze(1)   # for the counts only
-        x_max, _roi = self._prep(x_max, roi)
-        counts = (self._candidate_counts(x_max, _roi)[0] if self.rng_parity
-                  else self._candidate_counts_device(x_max, _roi))
-        out, cam_max = self._select(cams.detach().float().contiguous(), _roi, counts)
+        cams = cams.detach().float().contiguous()
+        if self.rng_parity:
+            # the draws must be sized like the reference's multinomial calls: the counts go through the host
+            x_max, _roi = self._prep(ops.temporal_cam_max(cams).unsqueeze(1), roi)
+            counts = self._candidate_counts(x_max, _roi)[0]
+        else:
+            counts = None
+            if self.use_roi and roi is None:   # the ROI is computed from the temporal max
+                _, _roi = self._prep(ops.temporal_cam_max(cams).unsqueeze(1), None)
+            elif self.use_roi:
+                assert torch.is_tensor(roi) and roi.ndim == 4 and roi.shape[1] == 1
+                assert roi.shape[0] == cams.shape[0] and roi.shape[2:] == cams.shape[2:]
+                _roi = self._erode(roi.to(cams.device)).long().contiguous()
+            else:
+                _roi = None
+        out, cam_max = self._select(cams, _roi, counts)
         return out.detach(), cam_max
 
     def use_all_roi(self, x: torch.Tensor, roi: torch.Tensor = None) -> torch.Tensor:

@@ -323,3 +323,58 @@ def test_temporal_kernels_match_the_reference_python(torch_cuda):
         size = tuple(int(v) for v in key[4:].split("x"))
         got = temporal.prepare_std_cams_disq(std, size).cpu().numpy()
         assert np.abs(got - g[key]).max() <= 1e-6, key
+
+
+def test_fused_and_two_kernel_paths(torch_cuda):
+    """Frames whose slice does not fit an SM's shared memory (tcam_seed_fused_supported == 0) and k > 32 take
+    tcam_seed_select + tcam_seed_labels; both paths are bit-exact against the reference restatement given its draws."""
+    torch = torch_cuda
+    import oracle.seeding as ref
+    from tcam_wsol_video_b200 import _lib
+    lib = _lib.load()
+    assert lib.tcam_seed_fused_supported(224 * 224, 1) == 1
+    assert lib.tcam_seed_fused_supported(224 * 224, 33) == 0
+    assert lib.tcam_seed_fused_supported(640 * 640, 1) == 0
+    for (b, h, w), kw in (((2, 640, 640), dict()), ((3, 48, 56), dict(min_=40, max_=35, ksz=1))):
+        cam, roi = _make(torch, b, h, w, seed=5)
+        mod = _seeder(**kw)
+        torch.manual_seed(11)
+        got = mod(cam, roi)
+        torch.manual_seed(11)
+        want = ref.tcam_seeder_forward(cam, roi, seed_tech=mod.seed_tech, min_=mod.min_, max_=mod.max_,
+                                       min_p=mod.min_p, max_p=mod.max_p, ksz=mod.ksz, ignore_idx=-255,
+                                       use_roi=mod.use_roi)
+        assert torch.equal(got, want)
+
+
+def test_in_kernel_draws(torch_cuda):
+    """rng_parity=False: the Exp(1) draws are made in the kernel (Philox keyed from torch's CUDA generator).  Same
+    torch seed -> same seeds; different seeds -> different picks; uniform sampling spreads over the candidates; weighted
+    sampling prefers high CAM values."""
+    torch = torch_cuda
+    cam, roi = _make(torch, 8, 96, 96, seed=9)
+    seeder = _seeder(rng_parity=False, ksz=1, seed_tech="seed_uniform")
+    torch.manual_seed(3)
+    a = seeder(cam, roi)
+    torch.manual_seed(3)
+    b = seeder(cam, roi)
+    assert torch.equal(a, b)
+    picks = []
+    for _ in range(40):
+        out = seeder(cam, roi)
+        assert ((out == 1).flatten(1).sum(1) == 1).all() and ((out == 0).flatten(1).sum(1) == 1).all()
+        picks.append((out[0] == 1).flatten().nonzero().item())
+    assert len(set(picks)) >= 30                                  # ~14 k candidates: repeats are unlikely
+    # weighted: the mean CAM value at the picks lies above the candidates' mean
+    flat = cam[0].flatten()
+    n_fg = int(np.float32(0.6) * np.float32(roi[0].sum().item()))
+    cand = torch.sort(flat * roi[0].flatten() + 1e-8, descending=True).values[:n_fg]
+    seeder_w = _seeder(rng_parity=False, ksz=1, seed_tech="seed_weighted")
+    vals = []
+    for _ in range(200):
+        out = seeder_w(cam, roi)
+        vals.append(flat[(out[0] == 1).flatten().nonzero().item()].item())
+    se = cand.std().item() / np.sqrt(200)
+    assert np.mean(vals) > cand.mean().item() + 1.0 * se
+    # every pick is a candidate
+    assert min(vals) + 1e-8 >= cand[-1].item() - 1e-12

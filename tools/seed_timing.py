@@ -25,3 +25,15 @@ for parity in (True, False):
           f"temporal max {timed(lambda: ops.temporal_cam_max(cams)):.3f} | prep {timed(lambda: seeder._prep(x_max, roi)):.3f} | "
           f"counts (host sync) {timed(lambda: seeder._candidate_counts(xm, r)):.3f} | draws {timed(lambda: seeder._draws(counts, dev)):.3f} | "
           f"select+labels {timed(lambda: seeder._select(cams, r, counts)):.3f}")
+
+# device time of the fused kernel alone (CUDA events)
+seeder = TCAMSeeder(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11, fg_erode_iter=0,
+                    ksz=3, support_background=True, multi_label_flag=False, seg_ignore_idx=-255, cuda_id=0,
+                    roi_method="roi_all", p_min_area_roi=0.05, use_roi=True, rng_parity=False)
+r = roi.long().contiguous()
+for _ in range(5): seeder._select(cams, r, None)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record()
+for _ in range(100): seeder._select(cams, r, None)
+e1.record(); torch.cuda.synchronize()
+print(f"_select (rng + fused kernel + allocations), device time: {e0.elapsed_time(e1) / 100:.4f} ms per call")
