@@ -385,6 +385,12 @@ __device__ __forceinline__ float load_pixel<uint8_t>(const void *base, size_t id
 #ifndef TCAMCRF_ADAPTIVE_TABLE
 #define TCAMCRF_ADAPTIVE_TABLE 1
 #endif
+// primary-tier slots per vertex of the previous call (rounded up to a power of two).  Measured, noise K=10, 32 frames:
+// 4 -> build 0.206 / neighbour 0.130 / clear 0.028 ms; 2 (tables of all frames fit the L2) -> 0.211 / 0.159 / 0.016;
+// 1 -> 0.343 / 0.481 / 0.036: the probe count matters, not where the table lives.
+#ifndef TCAMCRF_TABLE_HEADROOM
+#define TCAMCRF_TABLE_HEADROOM 4
+#endif
 // Clears the tables of `nc` frames: always the primary tier, the overflow tier only when the workspace is
 // new (magic mismatch) or the previous use spilled into it.  Also zeroes the per-frame vertex counters.
 __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ctrl, int frame0, int nc, int chunk,
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
     if (frame0 > 0) {
         eff = (unsigned int)ctrl[kCtrlEffSlots];
     } else if (!full) {
-        const unsigned int want = 4u * (unsigned int)ctrl[kCtrlPrevMax];
+        const unsigned int want = (unsigned int)TCAMCRF_TABLE_HEADROOM * (unsigned int)ctrl[kCtrlPrevMax];
         unsigned int e = geom.slots1 >> 4;   // floor: bounds what a bad guess costs (window-long probe chains)
         if (e < 4096u) e = 4096u;
         while (e < want && e < geom.slots1) e <<= 1;

@@ -231,6 +231,75 @@ def main():
         np.savez_compressed(os.path.join(OUT, "py_color_dense_crf_loss.npz"), image=cimg.numpy(),
                             seg=cseg.detach().numpy(), loss=closs.detach().numpy(), grad=cseg.grad.numpy(),
                             weight=np.float32(1e-3))
+    # --- GetRoiSingleCam (dlib/cams/tcam_seeding.py:316-430), the CPU ROI of a CAM, executed with REAL OpenCV (cv2 is in
+    #     this image): thresholding, component statistics and selection, cv2.findContours / boundingRect through the
+    #     reference's own compute_bboxes_from_scoremaps_ext_contours (dlib/utils/wsol.py:81-150) and get_largest_bbox
+    #     (tcam_seeding.py:34-41).  scikit-image is not installed: skimage.measure.label(connectivity=1) is stood in
+    #     for by scipy.ndimage.label (4-neighbour structure, raster-order numbering like skimage's) and
+    #     threshold_otsu by oracle/seeding.py's restatement of skimage 0.17.2 -- those two stay unpinned and are named
+    #     so in DESIGN.md.  np.float (removed from numpy 2) is mapped to float.
+    try:
+        import cv2
+        from scipy import ndimage
+
+        class _NP:
+            float = float
+
+            def __getattr__(self, name):
+                return getattr(np, name)
+
+        class _Measure:
+            @staticmethod
+            def label(blobs, background=0, connectivity=1, return_num=False):
+                assert connectivity == 1 and background == 0 and not return_num
+                return ndimage.label(blobs, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])[0]
+
+        wsrc = open(os.path.join(REF, "dlib/utils/wsol.py")).read()
+        wenv = {"np": np, "cv2": cv2, "Union": __import__("typing").Union,
+                "_CONTOUR_INDEX": 1 if cv2.__version__.split('.')[0] == '3' else 0}
+        for node in ast.parse(wsrc).body:
+            if isinstance(node, ast.FunctionDef) and node.name in ("check_scoremap_validity", "check_box_convention",
+                                                                   "compute_bboxes_from_scoremaps_ext_contours"):
+                exec(compile("\n".join(wsrc.splitlines()[node.lineno - 1:node.end_lineno]), "wsol.py", "exec"), wenv)
+        tsrc = open(os.path.join(REF, "dlib/cams/tcam_seeding.py")).read()
+        renv = {"np": _NP(), "torch": torch, "Tuple": Tuple, "constants": types.SimpleNamespace(
+                    ROI_SELECT=['roi_all', 'roi_high_density', 'largest'], ROI_ALL='roi_all',
+                    ROI_H_DENSITY='roi_high_density', ROI_LARGEST='largest'),
+                "measure": _Measure, "threshold_otsu": lambda a: oseed.threshold_otsu_skimage(a),
+                "compute_bboxes_from_scoremaps_ext_contours": wenv["compute_bboxes_from_scoremaps_ext_contours"],
+                "check_box_convention": wenv["check_box_convention"]}
+        for node in ast.parse(tsrc).body:
+            if isinstance(node, ast.FunctionDef) and node.name == "get_largest_bbox":
+                exec(compile("\n".join(tsrc.splitlines()[node.lineno - 1:node.end_lineno]), "tcam_seeding.py", "exec"), renv)
+        exec(compile(cut_class("dlib/cams/tcam_seeding.py", "GetRoiSingleCam"), "tcam_seeding.py:GetRoiSingleCam", "exec"),
+             renv)
+        gen = torch.Generator().manual_seed(91)
+        rois = {}
+        ci = 0
+        cj = 0
+        for (h, w, low_r) in ((48, 64, 6), (37, 53, 5), (96, 96, 9), (160, 144, 7)):
+            lowc = torch.rand((3, 1, low_r, low_r + 1), generator=gen)
+            cams = F.interpolate(lowc, size=(h, w), mode="bilinear", align_corners=False)[:, 0]
+            cams[1] = cams[1] * (torch.rand((h, w), generator=gen) > 0.35)      # speckle: many small components
+            for i in range(cams.shape[0]):
+                rois[f"cam{cj}"] = cams[i].numpy()
+                cj += 1
+                for method in ('roi_high_density', 'largest'):
+                    for thresh in (None, 0.55):
+                        getter = renv["GetRoiSingleCam"](roi_method=method, p_min_area_roi=0.05)
+                        roi_o, mask_o, bbox_o = getter(cams[i], thresh=thresh)
+                        rois[f"c{ci}_cfg"] = np.array([method, "" if thresh is None else str(thresh), str(cj - 1)])
+                        rois[f"c{ci}_roi"] = roi_o.numpy().astype(np.int8)
+                        rois[f"c{ci}_mask"] = mask_o.numpy().astype(np.int8)
+                        rois[f"c{ci}_bbox"] = bbox_o.numpy()
+                        ci += 1
+        rois["n_cases"] = np.int64(ci)
+        rois["cv2_version"] = np.array(cv2.__version__)
+        np.savez_compressed(os.path.join(OUT, "py_get_roi_single_cam.npz"), **rois)
+        print(f"wrote py_get_roi_single_cam.npz ({ci} cases, OpenCV {cv2.__version__})")
+    except ImportError as exc:
+        print("skipped py_get_roi_single_cam.npz:", exc)
+
     # --- clip grouping of the joint colour CRF (dlib/losses/tcam.py:32-45 group_ordered_frames, :207-232 pair_samples)
     src = open(os.path.join(REF, "dlib/losses/tcam.py")).read()
     gscope = {"torch": torch, "Tuple": Tuple}

@@ -378,3 +378,19 @@ def test_in_kernel_draws(torch_cuda):
     assert np.mean(vals) > cand.mean().item() + 1.0 * se
     # every pick is a candidate
     assert min(vals) + 1e-8 >= cand[-1].item() - 1e-12
+
+
+def test_roi_components_match_the_reference_class_run_with_opencv(torch_cuda):
+    """The GPU ROI kernels against the reference's own GetRoiSingleCam executed with real OpenCV (fixture made by
+    tests/golden/make_golden_py.py): masks, boxes and box masks identical in all 48 cases."""
+    import os
+    torch = torch_cuda
+    from tcam_wsol_video_b200.tcam_seeding import GetRoiSingleCam
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "py", "py_get_roi_single_cam.npz"))
+    for ci in range(int(g["n_cases"])):
+        method, thresh, cj = [str(v) for v in g[f"c{ci}_cfg"]]
+        cam = torch.from_numpy(g[f"cam{cj}"]).cuda()
+        roi, mask, bbox = GetRoiSingleCam(roi_method=method, p_min_area_roi=0.05)(cam, thresh=float(thresh) if thresh else None)
+        assert np.array_equal(roi.cpu().numpy(), g[f"c{ci}_roi"]), ci
+        assert np.array_equal(bbox.cpu().numpy(), g[f"c{ci}_bbox"]), ci
+        assert np.array_equal(mask.cpu().numpy(), g[f"c{ci}_mask"]), ci

@@ -232,3 +232,35 @@ def test_seeder_forward_restatement_matches_the_reference_module():
         assert np.array_equal(got.numpy(), g[f"case{ci}_out"]), ci
         ci += 1
     assert ci == 3
+
+
+def test_roi_restatement_matches_the_reference_class_run_with_opencv():
+    """oracle/seeding.py's GetRoiSingleCam restatement against the reference's own class (dlib/cams/tcam_seeding.py:
+    316-430) executed with REAL OpenCV 4.13 for the contour / bounding-rectangle part (tests/golden/make_golden_py.py;
+    skimage's label and Otsu stood in for, see there): 48 cases, both component modes, Otsu and fixed thresholds."""
+    from oracle import seeding as oseed
+    g = _py_golden("py_get_roi_single_cam.npz")
+    for ci in range(int(g["n_cases"])):
+        method, thresh, cj = [str(v) for v in g[f"c{ci}_cfg"]]
+        cam = g[f"cam{cj}"]
+        roi, mask, bbox = oseed.roi_components_single_cam(cam, method, 0.05, thresh=float(thresh) if thresh else None)
+        assert np.array_equal(roi, g[f"c{ci}_roi"]), ci
+        assert np.array_equal(bbox, g[f"c{ci}_bbox"]), ci
+        assert np.array_equal(mask, g[f"c{ci}_mask"]), ci
+
+
+def test_flat_dilation_agrees_with_opencv():
+    """kornia 0.6.4 (not installable here) documents its flat-kernel dilation as the max over the ksz x ksz window
+    anchored at ksz // 2 with the border ignored; OpenCV's cv2.dilate is an independent implementation of that same
+    operator (default anchor = kernel centre = ksz // 2, default border = ignored).  The restatement every seeding
+    test relies on (oracle/seeding.py flat_dilation) must agree with it, even kernel sizes included."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from oracle import seeding as oseed
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 3, 4, 5, 7):
+        x = (rng.random((2, 1, 23, 31)) > 0.9).astype(np.float32)
+        got = oseed.flat_dilation(torch.from_numpy(x), k).numpy()
+        for b in range(2):
+            want = cv2.dilate(x[b, 0], np.ones((k, k), np.uint8))
+            assert np.array_equal(got[b, 0], want), k
