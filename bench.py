@@ -703,6 +703,26 @@ def other_inputs(args, torch, dev, lib, N, K, local_rank):
         ms = timed_loop(torch, lambda i: seeder.forward_stack(cams, roi), 100, warmup=10)
         extra["tcam_seeder_forward_stack"] = {"ms_per_call": ms / 100, "samples": N, "frames_per_sample": 5,
                                               "what": "TCAMSeeder.forward_stack alone (temporal max + fg/bg seeds)"}
+        # the same step captured once in a CUDA graph and replayed (what a trainer does with torch.cuda.graphs): the
+        # ~25 launches of the step cost more on the CPU than on the GPU, the replay shows the GPU side alone
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    tcam_step(i)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            logits.grad = None
+            with torch.cuda.graph(graph):
+                tcam_step(0)
+            ms = timed_loop(torch, lambda i: graph.replay(), 100, warmup=10)
+            extra["tcam_seed_crf_step_natural_k2_cuda_graph"] = {
+                "value": N * 100 / (ms / 1e3), "unit": UNIT, "steps": 100, "ms_per_step": ms / 100,
+                "what": "the step above captured with torch.cuda.graph and replayed"}
+            del graph
+        except Exception as exc:
+            extra["tcam_seed_crf_step_natural_k2_cuda_graph"] = {"error": repr(exc)[:200]}
     except Exception as exc:  # context only; never fail the headline line
         extra["tcam_seed_crf_step_natural_k2"] = {"error": repr(exc)[:200]}
 

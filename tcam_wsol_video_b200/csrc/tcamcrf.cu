@@ -1848,6 +1848,7 @@ static int density_hint(void *ws)
 static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
 {
     if (!TCAMCRF_DENSITY_HINT) return;
+    if (stream_is_capturing(st)) return;   // (also: no pinned allocation while a capture is open)
     DensityHints &g_hints = g_hints_dev[current_device_slot()];
     std::lock_guard<std::mutex> lock(g_hints.mu);
     DensityHints::Slot *slot = g_hints.find(ws, true);
@@ -1856,7 +1857,6 @@ static void density_hint_refresh(const Plan &pl, char *ws, cudaStream_t st)
     // 0.25 ms steps); the first two calls on a workspace always refresh
     const unsigned int c = slot->calls++;
     if (c >= 2 && (c & 7u) != 0) return;
-    if (stream_is_capturing(st)) return;
     if (!g_hints.side) {   // this device's side stream, created on first use
         if (cudaStreamCreateWithFlags(&g_hints.side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&g_hints.ev, cudaEventDisableTiming) != cudaSuccess) {

@@ -51,14 +51,17 @@ class DenseCRFLossFunction(Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type='cuda')
-    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False, weight=1.0):
-        n = segmentations.shape[0]
+    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, exact_gradient=False, weight=1.0, batch_size=None):
+        # the reference divides by the local batch (dense_crf_loss.py:64); `batch_size` replaces it (a shard of a
+        # larger batch reports its share of the global mean, dist.ShardedCRFLoss)
+        n = segmentations.shape[0] if batch_size is None else batch_size
         cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy, loss_weight=weight)
         _lib.require_key_range(cfg, segmentations.shape[2], segmentations.shape[3])
         ctx.N = n
         ctx.weight = float(weight)
         ctx.exact = bool(exact_gradient)
-        if ctx.exact and n <= ops.lattice_capacity(cfg, segmentations.shape[1], *segmentations.shape[2:]):
+        if ctx.exact and segmentations.shape[0] <= ops.lattice_capacity(cfg, segmentations.shape[1],
+                                                                         *segmentations.shape[2:]):
             # keep the lattice: the backward pass runs the transposed filter on it (blur axes in reverse order)
             ctx.lattice = ops.Lattice(images, cfg, segmentations.shape[1], device=segmentations.device)
             ctx.segs = segmentations.detach()
@@ -88,7 +91,7 @@ class DenseCRFLossFunction(Function):
             grad_segmentation = ops.crf_backward((ctx.AS + ats) * 0.5, grad_output, float(ctx.N), ctx.weight)
         else:
             grad_segmentation = ops.crf_backward(ctx.AS, grad_output, float(ctx.N), ctx.weight)
-        return None, grad_segmentation, None, None, None, None
+        return None, grad_segmentation, None, None, None, None, None
 
 
 class DenseCRFLoss(nn.Module):
@@ -108,10 +111,14 @@ class DenseCRFLoss(nn.Module):
         self.scale_factor = scale_factor
         self.exact_gradient = exact_gradient
 
-    def forward(self, images, segmentations):
+    accepts_batch_size = True   # forward(..., batch_size=): see dist.ShardedCRFLoss
+
+    def forward(self, images, segmentations, batch_size=None):
         """
         :param images: N*3*H*W tensor with values in [0, 255]; CPU float32 (as in the reference) or CUDA float32/uint8.
         :param segmentations: softmaxed logits, N*K*H*W, CUDA.
+        :param batch_size: extension, None by default (reference behaviour: divide by N).  The batch size the sum is
+            divided by when these N frames are a shard of a larger batch.
         :return: loss tensor of shape [1] on segmentations.device.
         """
         scaled_images = _scale_images(images, self.scale_factor)
@@ -119,9 +126,11 @@ class DenseCRFLoss(nn.Module):
         w = _folded_weight(self.weight)
         if w is not None:   # weight * loss formed inside the loss kernels (same roundings, no extra launches)
             return DenseCRFLossFunction.apply(
-                scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient, w)
+                scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient, w,
+                batch_size)
         val = self.weight * DenseCRFLossFunction.apply(
-            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient)
+            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, self.exact_gradient, 1.0,
+            batch_size)
         return val
 
     def extra_repr(self):

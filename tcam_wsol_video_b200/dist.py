@@ -88,14 +88,18 @@ class ShardedCRFLoss(torch.nn.Module):
         """images/segmentations: this rank's shard.  Returns the loss: the global mean for ``"global"``, this rank's
         share of it for ``"global_async"`` (same gradient; the reduced value comes from ``global_loss()``), the local
         mean for ``"local"``.  Pass ``global_batch`` to skip the all-reduce that counts the frames."""
-        local = self.local_loss(images=images, segmentations=segmentations)
         if self.reduction == "local":
-            return local
+            return self.local_loss(images=images, segmentations=segmentations)
         n_local = segmentations.shape[0]
         if global_batch is None:
             global_batch = self._global_batch(n_local, segmentations.device)
-        # local = -sum_local / n_local  ->  this rank's share of the global mean = local * n_local / N
-        share = local * (float(n_local) / float(global_batch))
+        if getattr(self.local_loss, "accepts_batch_size", False):
+            # the loss kernels divide by the global batch directly: no extra multiply in forward or backward
+            share = self.local_loss(images=images, segmentations=segmentations, batch_size=int(global_batch))
+        else:
+            # local = -sum_local / n_local  ->  this rank's share of the global mean = local * n_local / N
+            local = self.local_loss(images=images, segmentations=segmentations)
+            share = local * (float(n_local) / float(global_batch))
         if self.reduction == "global":
             return all_reduce_scalar(share, self.group)
         self._pending = self._reduce_async(share.detach())

@@ -3,6 +3,7 @@ of one box, scalar loss all-reduce).  Needs >= 2 GPUs; skipped otherwise (the wo
 tests/test_dist_gloo.py cover the host logic on CPU)."""
 import json
 import os
+import re
 import socket
 import subprocess
 import sys
@@ -33,7 +34,9 @@ def test_sharded_crf_loss_over_nccl(n_total):
            os.path.join(ROOT, "tests", "dist_nccl_worker.py"), str(n_total)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
-    lines = [json.loads(ln.split(" ", 1)[1]) for ln in res.stdout.splitlines() if ln.startswith("NCCL_WORKER ")]
+    # the ranks share one stdout: two lines may arrive glued together
+    dec = json.JSONDecoder()
+    lines = [dec.raw_decode(res.stdout, m.end())[0] for m in re.finditer(r"NCCL_WORKER ", res.stdout)]
     assert len(lines) == world
     assert sorted((d["lo"], d["hi"]) for d in lines)[0][0] == 0 and max(d["hi"] for d in lines) == n_total
     for d in lines:

@@ -271,3 +271,59 @@ def test_colour_module_matches_the_reference_autograd_function(torch_cuda, pinne
     loss.backward()
     assert abs(loss.item() - float(g["loss"][0])) < REL_TOL * abs(float(g["loss"][0]))
     assert rel_err(seg.grad.cpu().numpy(), g["grad"]) < REL_TOL
+
+
+def test_tcam_step_in_a_cuda_graph(torch_cuda):
+    """The TCAM loss step -- temporal max + seeding (rng_parity=False: counts and draws in the kernel), CRF from logits,
+    cross-entropy on the seeds, backward -- captured with torch.cuda.graph on a stream the library has never seen (new
+    workspace, no density hint, no host round trip anywhere) and replayed on new inputs: same CRF gradient as eager."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.dense_crf_loss import DenseCRFLossFromLogits
+    from tcam_wsol_video_b200.tcam_seeding import TCAMSeeder
+    n, t, h, w = 4, 3, 64, 72
+    dev = torch.device("cuda", 0)
+    seeder = TCAMSeeder(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11, fg_erode_iter=0,
+                        ksz=3, support_background=True, multi_label_flag=False, seg_ignore_idx=-255, cuda_id=0,
+                        roi_method="roi_all", p_min_area_roi=0.05, use_roi=True, rng_parity=False)
+    crf = DenseCRFLossFromLogits(1.0, 15.0, 100.0, 1.0)
+    cams = torch.zeros((n, t, h, w), device=dev)
+    roi = torch.ones((n, 1, h, w), dtype=torch.long, device=dev)
+    img8 = torch.zeros((n, 3, h, w), dtype=torch.uint8, device=dev)
+    logits = torch.zeros((n, 2, h, w), device=dev, requires_grad=True)
+    seeds_out = torch.zeros((n, h, w), dtype=torch.long, device=dev)
+
+    def load(seed):
+        g = torch.Generator().manual_seed(seed)
+        cams.copy_(torch.rand((n, t, h, w), generator=g))
+        img8.copy_(torch.from_numpy(synth.make_images(n, h, w, "natural", seed=seed).astype(np.uint8)))
+        with torch.no_grad():
+            logits.copy_(torch.randn((n, 2, h, w), generator=g))
+
+    def step():
+        seeds, _ = seeder.forward_stack(cams, roi)
+        seeds_out.copy_(seeds)
+        l_crf = crf(images=img8, logits=logits)
+        loss = l_crf + torch.nn.functional.cross_entropy(logits, seeds, ignore_index=-255)
+        loss.backward()
+        return l_crf
+
+    load(1)
+    graph = torch.cuda.CUDAGraph()
+    logits.grad = None
+    with torch.cuda.graph(graph):
+        l_graph = step()
+    for seed in (2, 3):
+        load(seed)
+        logits.grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got_l = l_graph.item()
+        s = seeds_out.clone()
+        assert set(torch.unique(s).tolist()) <= {-255, 0, 1} and (s == 1).any() and (s == 0).any()
+        got = logits.grad.clone()
+        # eager: the same CRF term, and the cross-entropy on the seeds the replay picked
+        z = logits.detach().clone().requires_grad_(True)
+        l_e = crf(images=img8, logits=z)
+        (l_e + torch.nn.functional.cross_entropy(z, s, ignore_index=-255)).backward()
+        assert abs(got_l - l_e.item()) < 1e-5 * abs(l_e.item())
+        assert rel_err(got.cpu().numpy(), z.grad.cpu().numpy()) < 1e-5
