@@ -578,11 +578,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             ent["dram_gbs"] = c["dram_bytes"] / (per_launch_ms * 1e-3) / 1e9
             ent["frac_dram"] = ent["dram_gbs"] / peak
             ent["dram_over_algorithmic"] = c["dram_bytes"] / alg if alg > 0 else None
-            for k2 in ("lts_sectors", "lts_sectors_atom", "lts_sectors_red", "l1_global_requests"):
+            for k2 in ("lts_sectors", "lts_requests", "lts_requests_atom", "lts_requests_red", "l1_sectors_atom",
+                       "l1_sectors_red"):
                 if k2 in c:
                     ent[k2] = c[k2]
-            if c.get("l1_global_requests"):
-                ent["l1_requests_per_s"] = c["l1_global_requests"] / (per_launch_ms * 1e-3)
+            if c.get("lts_requests"):
+                # the L2-side view: requests and 32-byte sectors per second of the live launch (the kernels that only
+                # gather and stream -- blur, neighbour, slice -- all sit at ~190-220 G requests/s on B200) and ncu's
+                # own percentage of the sustained sector peak (measured under ncu, cold cache)
+                ent["lts_requests_per_s"] = c["lts_requests"] / (per_launch_ms * 1e-3)
+                ent["lts_sectors_per_s"] = c["lts_sectors"] / (per_launch_ms * 1e-3)
+                ent["lts_sectors_pct_of_peak_ncu"] = c.get("lts_sectors_pct_of_peak")
             step_dram += c["dram_bytes"] * launches_per_step
         stages[name] = ent
     dom = max(stages, key=lambda s_: stages[s_]["ms_per_step"]) if stages else None

@@ -5,8 +5,9 @@
 
 Per workload and pipeline stage (kernels mapped onto bench.py's stage names; the mean over the launches of a stage
 in the captured step): DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum), L2 sectors, L2 atomic / reduction
-sectors, L1 global-memory requests (loads + stores + atomics + reductions: the random-request rate is the bound the
-profiles/README argues for on dense lattices), launch time under ncu.  `source_sha` is bench.source_sha() of the build
+requests (compare-and-swap / ALU atomics, reductions) and their sectors at the L1, the L2's own sector count with its
+percentage of the hardware's sustained sector rate (the random-sector rate is the bound profiles/README argues for on
+dense lattices), warp-level global-memory requests, launch time under ncu.  `source_sha` is bench.source_sha() of the build
 that was captured: bench.py drops the file when the sources have changed since.
 """
 import csv
@@ -21,6 +22,8 @@ STAGE = (("prepare_kernel", "prepare"), ("build_dedup_kernel", "build"), ("build
          ("neighbour_kernel", "neighbour"), ("vertex_init_kernel", "splat"), ("splat_rows_kernel", "splat"),
          ("splat_kernel", "splat"), ("blur_kernel", "blur"), ("slice_kernel", "slice"),
          ("loss_backward_logits_kernel", "backward"), ("loss_backward_kernel", "backward"))
+FIELDS = ("dram_bytes", "lts_sectors", "lts_sectors_pct_of_peak", "lts_requests", "lts_requests_atom", "lts_requests_red",
+          "l1_sectors_atom", "l1_sectors_red", "l1_global_requests", "ncu_us")
 REQ = ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
        "l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum")
 
@@ -41,21 +44,24 @@ def parse(path):
         stage = next((s for k, s in STAGE if k in name), None)
         if stage is None:
             continue
-        a = acc.setdefault(stage, {"launches": 0, "dram_bytes": 0.0, "lts_sectors": 0.0, "lts_sectors_atom": 0.0,
-                                   "lts_sectors_red": 0.0, "l1_global_requests": 0.0, "ncu_us": 0.0, "kernels": set()})
+        a = acc.setdefault(stage, dict({k: 0.0 for k in FIELDS}, launches=0, kernels=set()))
         a["launches"] += 1
         a["kernels"].add(name.split("(")[0].replace("void ", ""))
         a["dram_bytes"] += (val(r, "dram__bytes_read.sum") or 0.0) + (val(r, "dram__bytes_write.sum") or 0.0)
         a["lts_sectors"] += val(r, "lts__t_sectors.sum") or 0.0
-        a["lts_sectors_atom"] += val(r, "lts__t_sectors_op_atom.sum") or 0.0
-        a["lts_sectors_red"] += val(r, "lts__t_sectors_op_red.sum") or 0.0
+        a["lts_sectors_pct_of_peak"] += val(r, "lts__t_sectors.sum.pct_of_peak_sustained_elapsed") or 0.0
+        a["lts_requests"] += val(r, "lts__t_requests.sum") or 0.0
+        a["lts_requests_atom"] += (val(r, "lts__t_requests_srcunit_tex_op_atom_dot_cas.sum") or 0.0) + \
+                                  (val(r, "lts__t_requests_srcunit_tex_op_atom_dot_alu.sum") or 0.0)
+        a["lts_requests_red"] += val(r, "lts__t_requests_srcunit_tex_op_red.sum") or 0.0
+        a["l1_sectors_atom"] += val(r, "l1tex__t_sectors_pipe_lsu_mem_global_op_atom.sum") or 0.0
+        a["l1_sectors_red"] += val(r, "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum") or 0.0
         a["l1_global_requests"] += sum(val(r, m) or 0.0 for m in REQ)
         a["ncu_us"] += val(r, "gpu__time_duration.sum") or 0.0
     out = {}
     for stage, a in acc.items():
         n = a["launches"]
-        out[stage] = {k: a[k] / n for k in ("dram_bytes", "lts_sectors", "lts_sectors_atom", "lts_sectors_red",
-                                           "l1_global_requests", "ncu_us")}
+        out[stage] = {k: a[k] / n for k in FIELDS}
         out[stage]["launches_in_capture"] = n
         out[stage]["kernels"] = sorted(a["kernels"])
     return out
