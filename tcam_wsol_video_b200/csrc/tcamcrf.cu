@@ -244,9 +244,10 @@ static int make_plan(const tcamcrf_config *cfg, int N, int K, int H, int W, Plan
     if (D < 1 || D > kMaxD) return fail(TCAMCRF_ERR_INVALID, "unsupported lattice dimension %d (1..%d)", D, kMaxD);
     if (N < 1 || K < 1 || H < 1 || W < 1) return fail(TCAMCRF_ERR_INVALID, "N,K,H,W must be positive");
     if ((long long)H * W > (1ll << 26)) return fail(TCAMCRF_ERR_INVALID, "image too large");
-    if (cfg->image_stride_planes < cfg->channels)
-        return fail(TCAMCRF_ERR_INVALID, "image_stride_planes (%d) < channels (%d)", cfg->image_stride_planes,
-                    cfg->channels);
+    // stride < channels: consecutive frames read overlapping windows of the image buffer -- what the reference's
+    // colour batch loop does for DIM > 3 (a fixed stride of 3 planes, colorbilateralfilter.cpp:50)
+    if (cfg->image_stride_planes < 1)
+        return fail(TCAMCRF_ERR_INVALID, "image_stride_planes (%d) must be positive", cfg->image_stride_planes);
     if (!(cfg->sigma_rgb > 0.f) || (cfg->feat == TCAMCRF_FEAT_XY_RGB && !(cfg->sigma_xy > 0.f)))
         return fail(TCAMCRF_ERR_INVALID, "sigmas must be positive");
     pl.D = D;
@@ -2307,9 +2308,14 @@ static int host_enqueue(HostCtx &g_host, const HostJob &j, HostTrace &trace, int
             // only the planes the kernels read: the very last image may be shorter than the stride
             // (the reference reads `channels` planes at a stride of 3, colorbilateralfilter.cpp:50)
             size_t img_floats = (size_t)fn * img_frame;
-            if (c0 + f0 + fn == N) img_floats = ((size_t)(fn - 1) * j.cfg.image_stride_planes + j.cfg.channels) * P;
-            CUDA_TRY(cudaMemcpyAsync(j.d_img + (size_t)(c0 + f0) * img_frame, j.images + (size_t)(c0 + f0) * img_frame,
-                                     img_floats * sizeof(float), cudaMemcpyHostToDevice, s_in));
+            size_t img_skip = 0;   // floats at the head of the section that the section before has already brought
+            if (c0 + f0 + fn == N || j.cfg.channels > j.cfg.image_stride_planes)
+                img_floats = ((size_t)(fn - 1) * j.cfg.image_stride_planes + j.cfg.channels) * P;
+            if (j.cfg.channels > j.cfg.image_stride_planes && c0 + f0 > 0)   // overlapping windows (see make_plan)
+                img_skip = (size_t)(j.cfg.channels - j.cfg.image_stride_planes) * P;
+            CUDA_TRY(cudaMemcpyAsync(j.d_img + (size_t)(c0 + f0) * img_frame + img_skip,
+                                     j.images + (size_t)(c0 + f0) * img_frame + img_skip,
+                                     (img_floats - img_skip) * sizeof(float), cudaMemcpyHostToDevice, s_in));
             CUDA_TRY(cudaEventRecord(ev_img, s_in));
             trace.mark("images in", c0 + f0, s_in);
             CUDA_TRY(cudaStreamWaitEvent(st, ev_img, 0));
@@ -2437,7 +2443,9 @@ static int host_run(const tcamcrf_config *cfg_in, const float *images, const flo
     const size_t P = (size_t)H * W;
     const size_t img_frame = (size_t)j.cfg.image_stride_planes * P;
     const size_t seg_frame = (size_t)K * P;
-    const size_t img_bytes = align_up((size_t)N * img_frame * sizeof(float), 256);
+    const size_t img_over = j.cfg.channels > j.cfg.image_stride_planes
+                                ? (size_t)(j.cfg.channels - j.cfg.image_stride_planes) * P : 0;   // overlapping windows
+    const size_t img_bytes = align_up(((size_t)N * img_frame + img_over) * sizeof(float), 256);
     const size_t seg_bytes = align_up((size_t)N * seg_frame * sizeof(float), 256);
     const size_t scal_bytes = align_up((size_t)(2 * ngroups + 2) * sizeof(float), 256);
     char *base = nullptr;
@@ -2735,6 +2743,9 @@ int tcamcrf_loss_forward_host_frames(const tcamcrf_config *cfg, const void *imag
                                      size_t workspace_bytes, void *cuda_stream)
 {
     if (!images_host || !images_stage_dev) return fail(TCAMCRF_ERR_INVALID, "null image pointer");
+    if (cfg && cfg->channels > cfg->image_stride_planes)
+        return fail(TCAMCRF_ERR_INVALID, "overlapping image windows (stride < channels) need device frames or the "
+                    "host-pointer API");
     if (logits && K < 2) return fail(TCAMCRF_ERR_INVALID, "softmax needs at least two classes");
     if (logits && !loss_dev) return fail(TCAMCRF_ERR_INVALID, "null loss pointer");
     return run_filter(cfg, images_u8 != 0, images_stage_dev, segs_dev, as_dev, loss_dev, N, K, H, W, n_norm, workspace,
@@ -2927,9 +2938,8 @@ int colorbilateralfilter_batch(float *images, int len_images, float *ins, int le
     // reads overlapping windows of `images`, which needs len_images >= ((N-1)*3 + DIM)*H*W.
     if (DIM > 3 && (long long)len_images < ((long long)(N - 1) * 3 + DIM) * H * W)
         return fail(TCAMCRF_ERR_INVALID, "images too short for DIM=%d with the reference's 3-plane stride", DIM);
-    if (DIM > 3 && N > 1)
-        return fail(TCAMCRF_ERR_INVALID, "DIM > 3 with N > 1 is not supported (overlapping 3-plane stride)");
-    tcamcrf_config c = ref_config(TCAMCRF_FEAT_COLOR, DIM, DIM > 3 ? DIM : 3, sigmargb, 1.f);
+    // stride 3 whatever DIM is: for DIM > 3 frame n reads planes [3n, 3n + DIM), like the reference
+    tcamcrf_config c = ref_config(TCAMCRF_FEAT_COLOR, DIM, 3, sigmargb, 1.f);
     return host_run(&c, images, ins, outs, nullptr, nullptr, N, K, H, W, 0.f);
 }
 

@@ -760,3 +760,18 @@ def test_colour_lattices_of_other_dimensions(torch_cuda, oracle_mod, tuning, dim
     want = oracle_mod.port_colorbilateralfilter_batch(img, seg, 1, k, h, w, 15.0, dim).reshape(seg.shape)
     got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=dim)
     _assert_close(got, want, f"colour lattice, DIM={dim}")
+
+
+@pytest.mark.parametrize("dim,n", [(4, 3), (6, 2), (5, 9), (2, 4), (1, 2)])
+def test_colour_batch_keeps_the_reference_three_plane_stride(torch_cuda, oracle_mod, dim, n):
+    """colorbilateralfilter_batch strides the image buffer by THREE planes whatever DIM is (colorbilateralfilter.cpp:50):
+    with DIM > 3 consecutive frames read overlapping windows [3n, 3n + DIM) of it, with DIM < 3 they skip planes.
+    Same here, through the drop-in host API, against the reference's own loop (oracle)."""
+    k, h, w = 2, 30, 34
+    rng = np.random.default_rng(dim * 10 + n)
+    planes = (n - 1) * 3 + max(dim, 3)
+    img = rng.integers(0, 256, size=(planes, h, w)).astype(np.float32)
+    seg = synth.make_segs(n, k, h, w, seed=dim)
+    want = oracle_mod.port_colorbilateralfilter_batch(img, seg, n, k, h, w, 15.0, dim).reshape(seg.shape)
+    got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=dim)
+    _assert_close(got, want, f"colour batch, DIM={dim}, N={n}")
