@@ -10,7 +10,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "tcam_wsol_video_b200", "csrc", "libtcamcrf.so")
 OUT = os.path.join(ROOT, "profiles", "sass")
-WANT = """build_kernelILi5Ef build_kernelILi5Eh build_kernelILi3Ef neighbour_kernelILi5E neighbour_kernelILi3E
+WANT = """build_kernelILi5Ef build_kernelILi5Eh build_kernelILi3Ef build_dedup_kernelILi5Ef build_dedup_kernelILi5Eh
+build_dedup_kernelILi3Ef seed_fused_kernel neighbour_kernelILi5E neighbour_kernelILi3E
 splat_kernelILi5ELi4ELb0E splat_kernelILi5ELi2ELb0E splat_kernelILi5ELi2ELb1E splat_rows_kernelILi5ELi3ELb0E
 blur_kernelILi4ELi3E blur_kernelILi4ELi1E blur_kernelILi2ELi1E
 slice_kernelILi5ELi4ELb0E slice_kernelILi5ELi2ELb0E loss_backward_kernel loss_backward_logits_kernel prepare_kernel
