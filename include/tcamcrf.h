@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TCAMCRF_VERSION 101
+#define TCAMCRF_VERSION 102
 
 /* host-side status codes */
 #define TCAMCRF_OK 0

@@ -1,5 +1,12 @@
-"""Pinned host<->device copy bandwidth of this box (context for the e2e numbers): python tools/pcie_bw.py"""
+"""Pinned host<->device copy bandwidth of this box (context for the e2e numbers): python tools/pcie_bw.py
+Under torchrun every rank measures its own GPU at the same time (the host ceiling with N GPUs busy)."""
+import os
 import torch
+rank, world = int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(rank)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 n = 64 << 20
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
 h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -22,4 +29,14 @@ def run(h2d, d2h, reps=10):
     e1.record(); torch.cuda.synchronize()
     return n * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
 run(True, True)
-print(f"h2d alone {run(True, False):.1f} GB/s, d2h alone {run(False, True):.1f} GB/s, both at once {run(True, True):.1f} GB/s each")
+if world > 1:
+    dist.barrier()
+a, b, c = run(True, False), run(False, True), run(True, True)
+print(f"rank {rank}/{world}: h2d alone {a:.1f} GB/s, d2h alone {b:.1f} GB/s, both at once {c:.1f} GB/s each", flush=True)
+if world > 1:
+    t = torch.tensor([a, b, c], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"all {world} ranks at once, summed: h2d {t[0].item():.0f} GB/s, d2h {t[1].item():.0f} GB/s, "
+              f"both ways {t[2].item():.0f} GB/s each way", flush=True)
+    dist.destroy_process_group()
