@@ -28,8 +28,9 @@ python tools/make_traffic.py $SHA "ncu --set full --clock-control none, one step
 cp profiles/traffic.json $O/${T}_traffic.json
 tail -5 $O/${T}_traffic.log
 # the bench lines (they read the traffic.json written above)
+t0=$SECONDS
 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err
-echo "bench rc=$?"
+echo "bench rc=$? wall $((SECONDS - t0)) s"
 python bench.py --kind natural --classes 2 --no-extra > $O/${T}_bench_natural_k2.json 2>> $O/${T}_bench.err
 python bench.py --classes 2 --no-extra > $O/${T}_bench_noise_k2.json 2>> $O/${T}_bench.err
 python bench.py --kind natural --no-extra > $O/${T}_bench_natural_k10.json 2>> $O/${T}_bench.err
