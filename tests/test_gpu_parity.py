@@ -775,3 +775,29 @@ def test_colour_batch_keeps_the_reference_three_plane_stride(torch_cuda, oracle_
     want = oracle_mod.port_colorbilateralfilter_batch(img, seg, n, k, h, w, 15.0, dim).reshape(seg.shape)
     got = _gpu_filter_host(img, seg, 15.0, 0.0, dim=dim)
     _assert_close(got, want, f"colour batch, DIM={dim}, N={n}")
+
+
+def test_soak_alternating_inputs_on_one_workspace(torch_cuda, oracle_mod):
+    """150 calls back to back on one workspace with the input regime changing under the library's feet: noise and
+    natural frames (the density hint flips the build / splat variants two calls late), class counts 1..12, a tiny
+    primary table tier every now and then (overflow tier in use, then clean again).  Every call must report status 0
+    and a finite loss; every 10th is compared with the oracle."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200 import ops
+    rng = np.random.default_rng(2024)
+    n, h, w = 4, 40, 56
+    checked = 0
+    for call in range(150):
+        kind = "noise" if (call // 7) % 2 == 0 else "natural"
+        k = int(rng.integers(1, 13))
+        load = 64.0 if call % 23 == 5 else 0.0
+        img = synth.make_images(n, h, w, kind, seed=1000 + call)
+        seg_np = synth.make_segs(n, k, h, w, seed=1000 + call)
+        cfg = _lib.make_config(_lib.FEAT_XY_RGB, 3, 15.0, 100.0, hash_load=load)
+        got, loss, ws = ops.crf_forward(torch.from_numpy(img).cuda(), torch.from_numpy(seg_np).cuda(), cfg, check=True)
+        assert torch.isfinite(loss).all(), call
+        if call % 10 == 0:
+            want = oracle_mod.port_bilateralfilter_batch(img, seg_np, n, k, h, w, 15.0, 100.0).reshape(seg_np.shape)
+            _assert_close(got.cpu().numpy(), want, f"call {call} ({kind}, K={k}, load {load})")
+            checked += 1
+    assert checked == 15
