@@ -709,6 +709,22 @@ def other_inputs(args, torch, dev, lib, N, K, local_rank):
         ms = timed_loop(torch, lambda i: seeder.forward_stack(cams, roi), 100, warmup=10)
         extra["tcam_seeder_forward_stack"] = {"ms_per_call": ms / 100, "samples": N, "frames_per_sample": 5,
                                               "what": "TCAMSeeder.forward_stack alone (temporal max + fg/bg seeds)"}
+        # the same step with the sparse seeds: FusedTcamLosses = CE on the labelled pixels + CRF as one autograd node
+        from tcam_wsol_video_b200.losses import ConRanFieldTcams, FusedTcamLosses, SelfLearningTcams
+        fused = FusedTcamLosses(SelfLearningTcams(cuda_id=local_rank, lambda_=1.0),
+                                ConRanFieldTcams(cuda_id=local_rank, lambda_=2e-9, sigma_rgb=SIGMA_RGB,
+                                                 sigma_xy=SIGMA_XY, scale_factor=1.0, fuse_softmax=True))
+
+        def tcam_step_fused(i):
+            logits.grad = None
+            seeds, _ = seeder.forward_stack(cams, roi, sparse=True)
+            fused(epoch=0, fcams=logits, raw_img=img8, seeds=seeds).backward()
+
+        ms = timed_loop(torch, tcam_step_fused, 100, warmup=10)
+        extra["tcam_seed_crf_step_natural_k2_fused"] = {
+            "value": N * 100 / (ms / 1e3), "unit": UNIT, "steps": 100, "ms_per_step": ms / 100,
+            "what": "the same step with TCAMSeeder(sparse=True) + FusedTcamLosses: no label map, the cross-entropy "
+                    "computed on the labelled pixels and added in place to the CRF gradient"}
         # the same step captured once in a CUDA graph and replayed (what a trainer does with torch.cuda.graphs): the
         # ~25 launches of the step cost more on the CPU than on the GPU, the replay shows the GPU side alone
         try:
@@ -725,7 +741,18 @@ def other_inputs(args, torch, dev, lib, N, K, local_rank):
             ms = timed_loop(torch, lambda i: graph.replay(), 100, warmup=10)
             extra["tcam_seed_crf_step_natural_k2_cuda_graph"] = {
                 "value": N * 100 / (ms / 1e3), "unit": UNIT, "steps": 100, "ms_per_step": ms / 100,
-                "what": "the step above captured with torch.cuda.graph and replayed"}
+                "what": "the (unfused) step captured with torch.cuda.graph and replayed"}
+            del graph
+            for i in range(3):
+                tcam_step_fused(i)
+            graph = torch.cuda.CUDAGraph()
+            logits.grad = None
+            with torch.cuda.graph(graph):
+                tcam_step_fused(0)
+            ms = timed_loop(torch, lambda i: graph.replay(), 100, warmup=10)
+            extra["tcam_seed_crf_step_natural_k2_fused_cuda_graph"] = {
+                "value": N * 100 / (ms / 1e3), "unit": UNIT, "steps": 100, "ms_per_step": ms / 100,
+                "what": "the fused step captured with torch.cuda.graph and replayed"}
             del graph
         except Exception as exc:
             extra["tcam_seed_crf_step_natural_k2_cuda_graph"] = {"error": repr(exc)[:200]}

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TCAMCRF_VERSION 102
+#define TCAMCRF_VERSION 103
 
 /* host-side status codes */
 #define TCAMCRF_OK 0
@@ -287,6 +287,22 @@ int tcam_seed_fused(const float *cams_dev, int T, const int64_t *roi_dev, const 
                     const int *n_cand_dev, const unsigned int *rng_dev, float max_p, int n_fg_fixed, int n_bg, int k_fg,
                     int k_bg, int weighted_fg, int B, int H, int W, int ksz, long long ignore_idx, float *cam_max_dev,
                     int *sel_dev, int kmax, int64_t *labels_dev, void *cuda_stream);
+
+/* Cross-entropy on the seeds without the label map: SelfLearningTcams (dlib/losses/tcam.py:48-77) =
+ * CrossEntropyLoss(ignore_index)(fcams, seeds) with 'mean' over the labelled pixels, and the labelled pixels are the
+ * ksz x ksz windows around the seeds in sel_dev [B,2,kmax] (side 0 = foreground -> class 1, side 1 = background ->
+ * class 0; a pixel both sides reach is ignored, tcam_seeding.py:239-254).  Same value and gradient as torch's call
+ * on tcam_seed_labels' map, from 2*kmax*ksz^2 work items per sample instead of four passes over [B,K,H,W].
+ * forward: scratch_dev = 1 + 2*B floats, zero before the first call (left clean); loss_dev [1] (NaN when nothing is
+ * labelled, like torch); count_dev [1] labelled pixels (kept for backward); optionally total_dev [1] = add_dev[0] +
+ * weight * loss (add_dev: another loss term already computed on the stream, e.g. the CRF's; may be NULL).
+ * backward: grad_logits_dev [B,K,H,W] += (grad_out * scale) * d loss / d logits  (in place, on top of whatever is there). */
+int tcam_seed_ce_forward(const float *logits_dev, const int *sel_dev, int kmax, int B, int K, int H, int W, int ksz,
+                         float *scratch_dev, float *loss_dev, float *count_dev, const float *add_dev, float weight,
+                         float *total_dev, void *cuda_stream);
+int tcam_seed_ce_backward(const float *logits_dev, const int *sel_dev, int kmax, int B, int K, int H, int W, int ksz,
+                          const float *count_dev, const float *grad_out_dev, float scale, float *grad_logits_dev,
+                          void *cuda_stream);
 
 /* ROI of every CAM of a batch by Otsu's threshold: roi = (cam*255 >= otsu(floor(cam*255))), 1/0 as int64, the
  * 'roi_all' branch of GetRoiSingleCam (dlib/cams/tcam_seeding.py:316-345,419-430; scikit-image threshold_otsu

@@ -129,6 +129,10 @@ SIGNATURES = {
                                  c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "tcam_otsu_roi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tcam_seed_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
+    "tcam_seed_ce_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "tcam_seed_ce_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_float, c_void_p, c_void_p]),
     "tcam_seed_fused_supported": (c_int, [c_int, c_int]),
     "tcam_seed_fused": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p,

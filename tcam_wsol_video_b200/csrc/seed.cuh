@@ -887,6 +887,145 @@ __global__ void __launch_bounds__(kSeedFusedThreads) seed_fused_kernel(const See
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cross-entropy on the seeds WITHOUT the label map (SelfLearningTcams, dlib/losses/tcam.py:48-77:
+// CrossEntropyLoss(ignore_index)(fcams, seeds), reduction 'mean' over the labelled pixels).
+//
+// The label map TCAMSeeder hands to the loss is ignore everywhere except the ksz x ksz windows around the
+// 2 x k selected seeds: 18 labelled pixels of 50 176 with the README recipe.  torch's cross-entropy still runs
+// log-softmax, NLL and both backward passes over the whole [B,K,H,W] tensor (12.8 MB at K = 2: 0.076 ms of a 0.41 ms
+// step).  Here the labelled pixels are enumerated from the selected seeds themselves: work item = (sample, side, seed,
+// window offset); a pixel counts once per side (the first seed whose window covers it) and is dropped when both
+// sides cover it -- exactly seed_labels_kernel's rule (tcam_seeding.py:239-254).  Same value and gradient as torch's
+// call on the label map; the sums run in a fixed order (one block per sample, ticketed final fold): deterministic.
+struct SeedCeParams {
+    const float *logits;   // [B][K][HW]
+    const int *sel;        // [B][2][kmax]
+    float *partial;        // [B][2]: loss sum, labelled pixels of the sample
+    int *ticket;           // [1], zero before the first call; left at zero
+    float *loss_out;       // [1]: mean over the labelled pixels of the batch (NaN when there is none, like torch)
+    float *count_out;      // [1]: labelled pixels of the batch
+    const float *add;      // optional [1]: another loss term (the CRF's), already on the stream
+    float *total_out;      // optional [1]: add + weight * loss
+    float weight;
+    int B, K, H, W, kmax, ksz;
+};
+
+// label of window pixel `off` of seed j on `side`, or -1 when the item does not count (outside the frame, an earlier
+// seed of the side already covers the pixel, or the other side covers it too); `pix` receives the pixel index
+__device__ __forceinline__ int seed_window_label(const int *sel_b, int kmax, int ksz, int H, int W, int side, int j,
+                                                 int off, int &pix)
+{
+    const int origin = ksz / 2, back = ksz - 1 - origin;
+    const int sp = sel_b[side * kmax + j];
+    if (sp < 0) return -1;
+    const int sy = sp / W, sx = sp - sy * W;
+    const int y = sy - back + off / ksz, x = sx - back + off % ksz;   // a seed at sy reaches [sy - back, sy + origin]
+    if (y < 0 || y >= H || x < 0 || x >= W) return -1;
+    pix = y * W + x;
+    auto covers = [&](int sd, int jj) {
+        const int q = sel_b[sd * kmax + jj];
+        if (q < 0) return false;
+        const int qy = q / W, qx = q - qy * W;
+        return y >= qy - back && y <= qy + origin && x >= qx - back && x <= qx + origin;
+    };
+    for (int jj = 0; jj < j; jj++)
+        if (covers(side, jj)) return -1;          // counted with the earlier seed
+    for (int jj = 0; jj < kmax; jj++)
+        if (covers(1 - side, jj)) return -1;      // claimed by both sides -> ignore
+    return side == 0 ? 1 : 0;                     // side 0 = foreground seeds -> class 1
+}
+
+__global__ void __launch_bounds__(256) seed_ce_forward_kernel(const SeedCeParams p)
+{
+    __shared__ float s_l[8];
+    __shared__ int s_c[8];
+    __shared__ bool s_last;
+    const int b = blockIdx.x;
+    const int HW = p.H * p.W;
+    const int *sel_b = p.sel + (size_t)b * 2 * p.kmax;
+    const float *z = p.logits + (size_t)b * p.K * HW;
+    const int win = p.ksz * p.ksz, items = 2 * p.kmax * win;
+    float lsum = 0.f;
+    int cnt = 0;
+    for (int it = threadIdx.x; it < items; it += 256) {
+        const int side = it / (p.kmax * win), rest = it - side * p.kmax * win;
+        int pix;
+        const int label = seed_window_label(sel_b, p.kmax, p.ksz, p.H, p.W, side, rest / win, rest % win, pix);
+        if (label < 0) continue;
+        float zmax = -INFINITY;
+        for (int k = 0; k < p.K; k++) zmax = fmaxf(zmax, __ldg(z + (size_t)k * HW + pix));
+        float sum = 0.f;
+        for (int k = 0; k < p.K; k++) sum += expf(__ldg(z + (size_t)k * HW + pix) - zmax);
+        lsum += (logf(sum) + zmax) - __ldg(z + (size_t)label * HW + pix);   // -log_softmax(z)[label]
+        cnt++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_l[threadIdx.x >> 5] = lsum;
+        s_c[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            lsum += s_l[w];
+            cnt += s_c[w];
+        }
+        p.partial[b * 2 + 0] = lsum;
+        p.partial[b * 2 + 1] = (float)cnt;
+        __threadfence();
+        s_last = atomicAdd(p.ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    float total = 0.f, n = 0.f;
+    for (int i = 0; i < p.B; i++) {   // fixed order
+        total += __ldcg(p.partial + i * 2);
+        n += __ldcg(p.partial + i * 2 + 1);
+    }
+    const float ce = __fdiv_rn(total, n);   // 0 / 0 = NaN: torch's mean over no element
+    p.loss_out[0] = ce;
+    p.count_out[0] = n;
+    if (p.total_out) p.total_out[0] = __fadd_rn(p.add ? p.add[0] : 0.f, __fmul_rn(ce, p.weight));
+    *p.ticket = 0;
+}
+
+// grad[b][k][pix] += (g * scale) * (softmax_k - [k == label]) / count   on the labelled pixels (every labelled pixel
+// belongs to exactly one work item: plain read-modify-write)
+__global__ void __launch_bounds__(256) seed_ce_backward_kernel(const float *__restrict__ logits,
+                                                               const int *__restrict__ sel, float *grad,
+                                                               const float *__restrict__ count,
+                                                               const float *__restrict__ grad_out, float scale, int K,
+                                                               int H, int W, int kmax, int ksz)
+{
+    const int b = blockIdx.x;
+    const int HW = H * W;
+    const int *sel_b = sel + (size_t)b * 2 * kmax;
+    const float *z = logits + (size_t)b * K * HW;
+    float *g = grad + (size_t)b * K * HW;
+    const float coef = __fdiv_rn(__fmul_rn(__ldg(grad_out), scale), __ldg(count));
+    const int win = ksz * ksz, items = 2 * kmax * win;
+    for (int it = threadIdx.x; it < items; it += 256) {
+        const int side = it / (kmax * win), rest = it - side * kmax * win;
+        int pix;
+        const int label = seed_window_label(sel_b, kmax, ksz, H, W, side, rest / win, rest % win, pix);
+        if (label < 0) continue;
+        float zmax = -INFINITY;
+        for (int k = 0; k < K; k++) zmax = fmaxf(zmax, __ldg(z + (size_t)k * HW + pix));
+        float sum = 0.f;
+        for (int k = 0; k < K; k++) sum += expf(__ldg(z + (size_t)k * HW + pix) - zmax);
+        for (int k = 0; k < K; k++) {
+            const float pk = __fdiv_rn(expf(__ldg(z + (size_t)k * HW + pix) - zmax), sum);
+            g[(size_t)k * HW + pix] += coef * (pk - (k == label ? 1.f : 0.f));
+        }
+    }
+}
+
 // out[b][y][x] = 1 if a fg seed dilates onto the pixel, 0 if a bg seed does, ignore if none or both
 __global__ void __launch_bounds__(256) seed_labels_kernel(const int *__restrict__ sel, int kmax, int B, int H, int W,
                                                           int ksz, long long ignore_idx, long long *__restrict__ out)

@@ -3144,6 +3144,51 @@ int tcam_seed_fused(const float *cams_dev, int T, const int64_t *roi_dev, const 
     return TCAMCRF_OK;
 }
 
+int tcam_seed_ce_forward(const float *logits_dev, const int *sel_dev, int kmax, int B, int K, int H, int W, int ksz,
+                         float *scratch_dev, float *loss_dev, float *count_dev, const float *add_dev, float weight,
+                         float *total_dev, void *cuda_stream)
+{
+    if (!logits_dev || !sel_dev || !scratch_dev || !loss_dev || !count_dev)
+        return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || K < 2 || H < 1 || W < 1 || kmax < 1 || ksz < 1)
+        return fail(TCAMCRF_ERR_INVALID, "B,H,W,kmax,ksz must be positive and K >= 2");
+    SeedCeParams sp;
+    sp.logits = logits_dev;
+    sp.sel = sel_dev;
+    sp.partial = scratch_dev + 1;
+    sp.ticket = reinterpret_cast<int *>(scratch_dev);
+    sp.loss_out = loss_dev;
+    sp.count_out = count_dev;
+    sp.add = add_dev;
+    sp.total_out = total_dev;
+    sp.weight = weight;
+    sp.B = B;
+    sp.K = K;
+    sp.H = H;
+    sp.W = W;
+    sp.kmax = kmax;
+    sp.ksz = ksz;
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    seed_ce_forward_kernel<<<B, 256, 0, (cudaStream_t)cuda_stream>>>(sp);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
+int tcam_seed_ce_backward(const float *logits_dev, const int *sel_dev, int kmax, int B, int K, int H, int W, int ksz,
+                          const float *count_dev, const float *grad_out_dev, float scale, float *grad_logits_dev,
+                          void *cuda_stream)
+{
+    if (!logits_dev || !sel_dev || !count_dev || !grad_out_dev || !grad_logits_dev)
+        return fail(TCAMCRF_ERR_INVALID, "null pointer argument");
+    if (B < 1 || K < 2 || H < 1 || W < 1 || kmax < 1 || ksz < 1)
+        return fail(TCAMCRF_ERR_INVALID, "B,H,W,kmax,ksz must be positive and K >= 2");
+    StageScope scope(kStSeed, 1, (cudaStream_t)cuda_stream);
+    seed_ce_backward_kernel<<<B, 256, 0, (cudaStream_t)cuda_stream>>>(logits_dev, sel_dev, grad_logits_dev, count_dev,
+                                                                     grad_out_dev, scale, K, H, W, kmax, ksz);
+    CUDA_TRY(cudaGetLastError());
+    return TCAMCRF_OK;
+}
+
 int tcam_seed_labels(const int *sel_dev, int kmax, int B, int H, int W, int ksz, long long ignore_idx,
                      int64_t *out_dev, void *cuda_stream)
 {

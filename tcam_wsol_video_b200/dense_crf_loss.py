@@ -18,7 +18,8 @@ from torch.autograd import Function
 
 from . import _lib, ops
 
-__all__ = ['DenseCRFLoss', 'DenseCRFLossFunction', 'DenseCRFLossFromLogits', 'DenseCRFLossFromLogitsFunction']
+__all__ = ['DenseCRFLoss', 'DenseCRFLossFunction', 'DenseCRFLossFromLogits', 'DenseCRFLossFromLogitsFunction',
+           'SeedCrossEntropyFunction', 'CrfAndSeedCEFromLogitsFunction']
 
 
 def _scale_images(images: torch.Tensor, scale_factor: float) -> torch.Tensor:
@@ -188,3 +189,54 @@ class DenseCRFLossFromLogits(nn.Module):
         return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}, fused_softmax=True'.format(
             self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor
         )
+
+
+class SeedCrossEntropyFunction(Function):
+    """``F.cross_entropy(logits, seeds, ignore_index=ignore)`` for seeds given as ``SparseSeeds`` (tcam_seeding.py): the
+    loss and its gradient come from the labelled pixels alone (csrc/seed.cuh, seed_ce_*_kernel)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, logits, sel, ksz):
+        logits = logits.detach().contiguous()
+        loss, count, _ = ops.seed_ce_forward(logits, sel, ksz)
+        ctx.logits, ctx.sel, ctx.ksz, ctx.count = logits, sel, int(ksz), count
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, grad_output):
+        grad = torch.zeros_like(ctx.logits)
+        ops.seed_ce_backward_(grad, ctx.logits, ctx.sel, ctx.ksz, ctx.count, grad_output)
+        return grad, None, None
+
+
+class CrfAndSeedCEFromLogitsFunction(Function):
+    """``crf_weight * DenseCRFLoss(softmax(logits)) + ce_weight * cross_entropy(logits, seeds)`` as ONE autograd node:
+    the two terms of TCAM's loss that read the decoder's logits (dlib/losses/tcam.py:48-115).  The backward pass writes
+    the CRF gradient through the softmax (one kernel) and adds the cross-entropy's on the handful of labelled pixels
+    in place -- no second dense gradient, no accumulation pass.  Returns (total, crf term, unweighted cross-entropy);
+    only the total carries a gradient."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, images, logits, sigma_rgb, sigma_xy, crf_weight, sel, ksz, ce_weight):
+        n = logits.shape[0]
+        cfg = _lib.make_config(ops.FEAT_XY_RGB, 3, sigma_rgb, sigma_xy, loss_weight=crf_weight)
+        _lib.require_key_range(cfg, logits.shape[2], logits.shape[3])
+        logits = logits.detach().contiguous()
+        as_t, crf_loss, _ = ops.crf_forward_logits(images, logits, cfg, n_norm=float(n))
+        # the kernel that finishes the cross-entropy also forms total = crf + ce_weight * ce: no torch glue launches
+        ce_loss, count, total = ops.seed_ce_forward(logits, sel, ksz, add=crf_loss, weight=float(ce_weight))
+        ctx.AS, ctx.logits, ctx.N = as_t, logits, n
+        ctx.crf_weight, ctx.ce_weight = float(crf_weight), float(ce_weight)
+        ctx.sel, ctx.ksz, ctx.count = sel, int(ksz), count
+        ctx.mark_non_differentiable(crf_loss, ce_loss)
+        return total, crf_loss, ce_loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, grad_total, _g_crf, _g_ce):
+        grad = ops.crf_backward_logits(ctx.AS, ctx.logits, grad_total, float(ctx.N), ctx.crf_weight)
+        ops.seed_ce_backward_(grad, ctx.logits, ctx.sel, ctx.ksz, ctx.count, grad_total, ctx.ce_weight)
+        return None, grad, None, None, None, None, None, None

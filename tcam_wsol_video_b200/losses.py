@@ -16,9 +16,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .color_dense_crf_loss import ColorDenseCRFLoss
-from .dense_crf_loss import DenseCRFLoss, DenseCRFLossFromLogits
+from .dense_crf_loss import (CrfAndSeedCEFromLogitsFunction, DenseCRFLoss, DenseCRFLossFromLogits,
+                             SeedCrossEntropyFunction, _folded_weight)
+from .tcam_seeding import SparseSeeds
 
-__all__ = ['ElementaryLoss', 'ConRanFieldTcams', 'RgbJointConRanFieldTcams', 'SelfLearningTcams',
+__all__ = ['ElementaryLoss', 'ConRanFieldTcams', 'RgbJointConRanFieldTcams', 'SelfLearningTcams', 'FusedTcamLosses',
            'group_ordered_frames']
 
 
@@ -102,9 +104,15 @@ class SelfLearningTcams(ElementaryLoss):
         self.loss = nn.CrossEntropyLoss(reduction="mean", ignore_index=self.seg_ignore_idx).to(self._device)
 
     def forward(self, epoch=0, fcams=None, seeds=None, **kwargs):
+        """``seeds``: the reference's [B,H,W] long map, or (extension) the seeder's ``SparseSeeds``: the same loss and
+        gradient computed from the labelled pixels alone."""
         super(SelfLearningTcams, self).forward(epoch=epoch)
         if not self.is_on():
             return self._zero
+        if isinstance(seeds, SparseSeeds):
+            if seeds.ignore_idx != self.seg_ignore_idx:
+                raise ValueError('seeds were made with another ignore index')
+            return SeedCrossEntropyFunction.apply(fcams, seeds.sel, seeds.ksz) * self.lambda_
         return self.loss(input=fcams, target=seeds) * self.lambda_
 
 
@@ -130,6 +138,33 @@ class ConRanFieldTcams(ElementaryLoss):
         if self.loss_from_logits is not None and fcams.shape[1] > 1:
             return self.loss_from_logits(images=raw_img, logits=fcams)
         return self.loss(images=raw_img, segmentations=_probabilities(fcams))
+
+
+class FusedTcamLosses(nn.Module):
+    """``SelfLearningTcams`` + ``ConRanFieldTcams`` as one autograd node (extension; same value and gradient as the sum
+    of the two modules, tests/test_gpu_losses.py::test_fused_tcam_losses).  Takes the two loss objects (their lambdas,
+    bandwidths and epoch windows are honoured) and, per step, the decoder's logits, the raw frames and the seeder's
+    ``SparseSeeds``.  Falls back to the separate modules whenever a term is off, the CRF rescales its inputs, the
+    weights are not plain numbers or the maps have a single channel."""
+
+    def __init__(self, self_learning: SelfLearningTcams, con_ran_field: ConRanFieldTcams):
+        super(FusedTcamLosses, self).__init__()
+        self.sl = self_learning
+        self.crf = con_ran_field
+
+    def forward(self, epoch=0, fcams=None, raw_img=None, seeds=None, **kwargs):
+        self.sl.c_epoch = epoch
+        self.crf.c_epoch = epoch
+        w_crf, w_sl = _folded_weight(self.crf.lambda_), _folded_weight(self.sl.lambda_)
+        fusable = (self.sl.is_on() and self.crf.is_on() and isinstance(seeds, SparseSeeds) and fcams.shape[1] > 1
+                   and self.crf.scale_factor == 1.0 and w_crf is not None and w_sl is not None
+                   and seeds.ignore_idx == self.sl.seg_ignore_idx)
+        if not fusable:
+            return self.sl(epoch=epoch, fcams=fcams, seeds=seeds) + self.crf(epoch=epoch, fcams=fcams, raw_img=raw_img)
+        total, self.last_crf, ce = CrfAndSeedCEFromLogitsFunction.apply(
+            raw_img, fcams, self.crf.sigma_rgb, self.crf.sigma_xy, w_crf, seeds.sel, seeds.ksz, w_sl)
+        self.last_ce = ce           # the unweighted cross-entropy; last_crf is the weighted CRF term (for logging)
+        return total
 
 
 class RgbJointConRanFieldTcams(ElementaryLoss):

@@ -351,6 +351,46 @@ def crf_backward(as_t: torch.Tensor, grad_output: torch.Tensor, n_norm: float, w
     return grad
 
 
+_seed_ce_scratch: Dict[Tuple[int, int, int], torch.Tensor] = {}
+
+
+def seed_ce_forward(logits: torch.Tensor, sel: torch.Tensor, ksz: int, add: Optional[torch.Tensor] = None,
+                    weight: float = 1.0):
+    """Cross-entropy of `logits` [B,K,H,W] on the seeds `sel` [B,2,kmax] (see tcam_seed_ce_forward): returns
+    (loss [1], count [1] float32 = labelled pixels, total [1] = add + weight * loss or None without `add`)."""
+    lib = _lib.load()
+    _require_cuda(logits, "logits")
+    b, k, h, w = logits.shape
+    device = logits.device
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device), b)
+    scratch = _seed_ce_scratch.get(key)
+    if scratch is None or torch.cuda.is_current_stream_capturing():
+        scratch = torch.zeros(1 + 2 * b, dtype=torch.float32, device=device)    # ticket + per-sample partials
+        if not torch.cuda.is_current_stream_capturing():
+            _seed_ce_scratch[key] = scratch
+    out = torch.empty(3, dtype=torch.float32, device=device)     # loss, count, total
+    with torch.cuda.device(device):
+        _lib.check(lib.tcam_seed_ce_forward(logits.data_ptr(), sel.data_ptr(), int(sel.shape[2]), b, k, h, w, int(ksz),
+                                            scratch.data_ptr(), out.data_ptr(), out.data_ptr() + 4,
+                                            add.data_ptr() if add is not None else None, float(weight),
+                                            out.data_ptr() + 8 if add is not None else None, _stream_ptr(device)),
+                   "tcam_seed_ce_forward")
+    return out[0:1], out[1:2], (out[2:3] if add is not None else None)
+
+
+def seed_ce_backward_(grad_logits: torch.Tensor, logits: torch.Tensor, sel: torch.Tensor, ksz: int, count: torch.Tensor,
+                      grad_output: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """grad_logits += (grad_output * scale) * d CE / d logits, in place on the labelled pixels."""
+    lib = _lib.load()
+    b, k, h, w = logits.shape
+    g = grad_output.detach().reshape(-1)[:1].to(device=logits.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.tcam_seed_ce_backward(logits.data_ptr(), sel.data_ptr(), int(sel.shape[2]), b, k, h, w, int(ksz),
+                                             count.data_ptr(), g.data_ptr(), float(scale), grad_logits.data_ptr(),
+                                             _stream_ptr(logits.device)), "tcam_seed_ce_backward")
+    return grad_logits
+
+
 def temporal_cam_max(cams: torch.Tensor, renorm_h: float = 0.0) -> torch.Tensor:
     """max over dim 1 of a CUDA float32 stack [B,T,...] -> [B,...] with torch.maximum's NaN propagation.
 
@@ -444,5 +484,5 @@ def roi_components(cams: torch.Tensor, largest_only: bool, p_min_area: float, th
     return roi, mask, bbox.float()
 
 
-__all__ = ["Lattice", "otsu_roi", "roi_components", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "prepare_std_cams", "workspace_status", "release_workspaces",
+__all__ = ["Lattice", "seed_ce_forward", "seed_ce_backward_", "otsu_roi", "roi_components", "crf_filter_transposed", "crf_forward", "crf_backward", "crf_forward_logits", "crf_backward_logits", "temporal_cam_max", "prepare_std_cams", "workspace_status", "release_workspaces",
            "FEAT_COLOR", "FEAT_XY_RGB"]

@@ -33,7 +33,7 @@ import torch.nn.functional as F
 
 from . import _lib, ops
 
-__all__ = ['TCAMSeeder', 'GetRoiSingleCam', 'SEED_UNIFORM', 'SEED_WEIGHTED', 'ROI_ALL', 'ROI_H_DENSITY', 'ROI_LARGEST']
+__all__ = ['TCAMSeeder', 'SparseSeeds', 'GetRoiSingleCam', 'SEED_UNIFORM', 'SEED_WEIGHTED', 'ROI_ALL', 'ROI_H_DENSITY', 'ROI_LARGEST']
 
 # dlib/configure/constants.py:352-354,368-372
 SEED_UNIFORM = 'seed_uniform'
@@ -43,6 +43,31 @@ ROI_ALL = 'roi_all'
 ROI_H_DENSITY = 'roi_high_density'
 ROI_LARGEST = 'largest'
 ROI_SELECT = [ROI_ALL, ROI_H_DENSITY, ROI_LARGEST]
+
+
+class SparseSeeds(object):
+    """The seeder's output before it is painted into a label map: the selected pixel indices ``sel`` [B,2,kmax] int32
+    (side 0 = foreground, 1 = background, -1 = unused) with the dilation size and the ignore index that turn them into
+    labels.  ``SelfLearningTcams`` / ``FusedTcamLosses`` take it as ``seeds`` and compute the cross-entropy from the
+    2*kmax*ksz^2 labelled pixels per sample directly (the map is 99.96 % ignore with the README recipe); ``dense()``
+    paints the reference's [B,H,W] long map when something else needs it."""
+
+    def __init__(self, sel: torch.Tensor, ksz: int, ignore_idx: int, h: int, w: int):
+        self.sel, self.ksz, self.ignore_idx, self.h, self.w = sel, int(ksz), int(ignore_idx), int(h), int(w)
+
+    @property
+    def kmax(self) -> int:
+        return int(self.sel.shape[2])
+
+    def dense(self) -> torch.Tensor:
+        lib = _lib.load()
+        b = self.sel.shape[0]
+        out = torch.empty((b, self.h, self.w), dtype=torch.long, device=self.sel.device)
+        with torch.cuda.device(self.sel.device):
+            _lib.check(lib.tcam_seed_labels(self.sel.data_ptr(), self.kmax, b, self.h, self.w, self.ksz, self.ignore_idx,
+                                            out.data_ptr(), torch.cuda.current_stream(self.sel.device).cuda_stream),
+                       'tcam_seed_labels')
+        return out
 
 
 class TCAMSeeder(nn.Module):
@@ -184,7 +209,7 @@ class TCAMSeeder(nn.Module):
             q.exponential_(1)
         return q, offsets
 
-    def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts):
+    def _select(self, cams: torch.Tensor, roi: Optional[torch.Tensor], counts, sparse: bool = False):
         """cams [B,T,H,W] float32 CUDA -> (labels [B,H,W] long, cam_max [B,H,W]).  counts: numpy [B,2] (draws sized and
         ordered like the reference's multinomial calls) or None (no host round trip: counts and draws are made by the
         kernel)."""
@@ -211,7 +236,7 @@ class TCAMSeeder(nn.Module):
                 q_off, n_cand = meta[: 2 * b], meta[2 * b:]
         cam_max = torch.empty((b, h, w), dtype=torch.float32, device=device)
         sel = torch.empty((b, 2, kmax), dtype=torch.int32, device=device)
-        out = torch.empty((b, h, w), dtype=torch.long, device=device)
+        out = None if sparse else torch.empty((b, h, w), dtype=torch.long, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
             if fused:
@@ -221,7 +246,8 @@ class TCAMSeeder(nn.Module):
                     n_cand.data_ptr() if n_cand is not None else None, rng.data_ptr() if rng is not None else None,
                     float(np.float32(self.max_p)), n_fg_fixed, n_bg, self.max_, self.min_,
                     1 if self.seed_tech == SEED_WEIGHTED else 0, b, h, w, self.ksz, int(self.ignore_idx),
-                    cam_max.data_ptr(), sel.data_ptr(), kmax, out.data_ptr(), stream), 'tcam_seed_fused')
+                    cam_max.data_ptr(), sel.data_ptr(), kmax, out.data_ptr() if out is not None else None, stream),
+                    'tcam_seed_fused')
             else:
                 scratch = torch.empty((b, 2, h * w), dtype=torch.float32, device=device)
                 _lib.check(lib.tcam_seed_select(cams.data_ptr(), t, roi.data_ptr() if roi is not None else None,
@@ -229,9 +255,12 @@ class TCAMSeeder(nn.Module):
                                                 1 if self.seed_tech == SEED_WEIGHTED else 0, b, h * w,
                                                 cam_max.data_ptr(), scratch.data_ptr(), sel.data_ptr(), kmax, stream),
                            'tcam_seed_select')
-                _lib.check(lib.tcam_seed_labels(sel.data_ptr(), kmax, b, h, w, self.ksz, int(self.ignore_idx),
-                                                out.data_ptr(), stream), 'tcam_seed_labels')
+                if out is not None:
+                    _lib.check(lib.tcam_seed_labels(sel.data_ptr(), kmax, b, h, w, self.ksz, int(self.ignore_idx),
+                                                    out.data_ptr(), stream), 'tcam_seed_labels')
         self._last_sel = sel
+        if sparse:
+            return SparseSeeds(sel, self.ksz, int(self.ignore_idx), h, w), cam_max
         return out, cam_max
 
     def _prep(self, x: torch.Tensor, roi: Optional[torch.Tensor]):
@@ -259,15 +288,16 @@ class TCAMSeeder(nn.Module):
         return x.detach().float().contiguous(), _roi
 
     # -- reference API -----------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, roi: torch.Tensor = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, roi: torch.Tensor = None, sparse: bool = False):
+        """``sparse=True`` (extension): return the ``SparseSeeds`` instead of painting the [B,H,W] label map."""
         x, _roi = self._prep(x, roi)
         b, d, h, w = x.shape
         assert d == 1, d  # todo multilabel.
         counts = self._candidate_counts(x, _roi)[0] if self.rng_parity else None
-        out, _ = self._select(x, _roi, counts)
-        return out.detach()
+        out, _ = self._select(x, _roi, counts, sparse=sparse)
+        return out if sparse else out.detach()
 
-    def forward_stack(self, cams: torch.Tensor, roi: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_stack(self, cams: torch.Tensor, roi: torch.Tensor = None, sparse: bool = False):
         """Fused temporal max + seeding: cams [B,T,H,W] (current frame and its neighbours' CAMs at the same
         resolution).  Returns (seeds [B,H,W] long, cam_max [B,H,W]); identical to
         ``forward(cams.max-chain over T)`` (dlib/datasets/wsol_loader.py:591-600 followed by TCAMSeeder)."""
@@ -287,8 +317,8 @@ class TCAMSeeder(nn.Module):
                 _roi = self._erode(roi.to(cams.device)).long().contiguous()
             else:
                 _roi = None
-        out, cam_max = self._select(cams, _roi, counts)
-        return out.detach(), cam_max
+        out, cam_max = self._select(cams, _roi, counts, sparse=sparse)
+        return (out if sparse else out.detach()), cam_max
 
     def use_all_roi(self, x: torch.Tensor, roi: torch.Tensor = None) -> torch.Tensor:
         """Every roi pixel becomes foreground, everything else ignore (tcam_seeding.py:258-299)."""

@@ -327,3 +327,85 @@ def test_tcam_step_in_a_cuda_graph(torch_cuda):
         (l_e + torch.nn.functional.cross_entropy(z, s, ignore_index=-255)).backward()
         assert abs(got_l - l_e.item()) < 1e-5 * abs(l_e.item())
         assert rel_err(got.cpu().numpy(), z.grad.cpu().numpy()) < 1e-5
+
+
+def _seeder_kw(**kw):
+    base = dict(seed_tech="seed_weighted", min_=1, max_=1, max_p=0.6, min_p=0.1, fg_erode_k=11, fg_erode_iter=0,
+                ksz=3, support_background=True, multi_label_flag=False, seg_ignore_idx=-255, cuda_id=0,
+                roi_method="roi_all", p_min_area_roi=0.05, use_roi=True)
+    base.update(kw)
+    return base
+
+
+@pytest.mark.parametrize("cfg,shape,k_classes", [
+    (dict(), (4, 64, 72), 2),
+    (dict(min_=3, max_=5, ksz=5), (3, 40, 44), 2),            # overlapping windows, fg/bg conflicts
+    (dict(min_=6, max_=6, ksz=4, min_p=0.3, max_p=0.3), (2, 12, 14), 2),   # even window, seeds at the borders
+    (dict(min_=2, max_=0, ksz=3), (3, 33, 35), 4),            # background seeds only, four channels
+])
+def test_sparse_seed_cross_entropy(torch_cuda, cfg, shape, k_classes):
+    """SelfLearningTcams on SparseSeeds (the cross-entropy computed from the labelled pixels alone) against torch's
+    CrossEntropyLoss on the label map the same seeds paint (dlib/losses/tcam.py:48-77): value and gradient."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.losses import SelfLearningTcams
+    from tcam_wsol_video_b200.tcam_seeding import SparseSeeds, TCAMSeeder
+    b, h, w = shape
+    g = torch.Generator().manual_seed(b * 100 + h)
+    low = torch.rand((b, 1, 7, 7), generator=g)
+    cam = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False).cuda()
+    cam[b - 1] = 0.5                                           # a flat CAM: no seeds for that sample
+    roi = (cam >= cam.flatten(1).median(dim=1).values.view(b, 1, 1, 1)).long()
+    seeder = TCAMSeeder(**_seeder_kw(**cfg))
+    torch.manual_seed(7)
+    dense = seeder(cam, roi)
+    torch.manual_seed(7)
+    sparse = seeder(cam, roi, sparse=True)
+    assert isinstance(sparse, SparseSeeds) and torch.equal(sparse.dense(), dense)
+    sl = SelfLearningTcams(cuda_id=0, lambda_=0.7)
+    z1 = torch.randn((b, k_classes, h, w), generator=g).cuda().requires_grad_(True)
+    z2 = z1.detach().clone().requires_grad_(True)
+    l_sparse = sl(fcams=z1, seeds=sparse)
+    l_dense = sl(fcams=z2, seeds=dense)
+    l_sparse.backward()
+    l_dense.backward()
+    assert abs(l_sparse.item() - l_dense.item()) < 1e-6 * abs(l_dense.item())
+    assert rel_err(z1.grad.cpu().numpy(), z2.grad.cpu().numpy()) < 1e-6
+    # nothing labelled at all: NaN, like torch's mean over no element
+    none = SparseSeeds(torch.full_like(sparse.sel, -1), sparse.ksz, -255, h, w)
+    assert torch.isnan(sl(fcams=z1.detach(), seeds=none)).all()
+
+
+def test_fused_tcam_losses(torch_cuda):
+    """FusedTcamLosses: SelfLearningTcams + ConRanFieldTcams as one autograd node (sparse cross-entropy added in place
+    to the CRF gradient).  Same total, same terms, same gradient as the two modules run separately on the label map;
+    epoch gating of either term falls back to the separate modules."""
+    torch = torch_cuda
+    from tcam_wsol_video_b200.losses import ConRanFieldTcams, FusedTcamLosses, SelfLearningTcams
+    from tcam_wsol_video_b200.tcam_seeding import TCAMSeeder
+    b, h, w = 5, 48, 56
+    g = torch.Generator().manual_seed(3)
+    low = torch.rand((b, 3, 7, 7), generator=g)
+    cams = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False).cuda()
+    roi = torch.ones((b, 1, h, w), dtype=torch.long, device="cuda")
+    raw = torch.from_numpy(synth.make_images(b, h, w, "natural", seed=8).astype(np.uint8)).cuda()
+    seeder = TCAMSeeder(**_seeder_kw(min_=2, max_=2, ksz=3, rng_parity=False))
+    seeds, _ = seeder.forward_stack(cams, roi, sparse=True)
+    sl = SelfLearningTcams(cuda_id=0, lambda_=1.0)
+    crf = ConRanFieldTcams(cuda_id=0, lambda_=2e-9, sigma_rgb=15., sigma_xy=100., scale_factor=1.0, fuse_softmax=True)
+    fused = FusedTcamLosses(sl, crf)
+    z1 = torch.randn((b, 2, h, w), generator=g).cuda().requires_grad_(True)
+    z2 = z1.detach().clone().requires_grad_(True)
+    total = fused(epoch=0, fcams=z1, raw_img=raw, seeds=seeds)
+    total.backward()
+    want_sl = sl(epoch=0, fcams=z2, seeds=seeds.dense())
+    want_crf = crf(epoch=0, fcams=z2, raw_img=raw)
+    (want_sl + want_crf).backward()
+    assert abs(total.item() - (want_sl + want_crf).item()) < 1e-6 * abs((want_sl + want_crf).item())
+    assert abs(fused.last_ce.item() * sl.lambda_ - want_sl.item()) < 1e-6 * abs(want_sl.item())
+    assert abs(fused.last_crf.item() - want_crf.item()) < 1e-5 * abs(want_crf.item())
+    assert rel_err(z1.grad.cpu().numpy(), z2.grad.cpu().numpy()) < 1e-5
+    # the CRF term switched off by its epoch window: the fused module returns the cross-entropy alone
+    crf_late = ConRanFieldTcams(cuda_id=0, lambda_=2e-9, sigma_rgb=15., sigma_xy=100., scale_factor=1.0,
+                                fuse_softmax=True, start_epoch=5, end_epoch=9)
+    only_sl = FusedTcamLosses(sl, crf_late)(epoch=0, fcams=z1.detach(), raw_img=raw, seeds=seeds)
+    assert abs(only_sl.item() - want_sl.item()) < 1e-6 * abs(want_sl.item())
