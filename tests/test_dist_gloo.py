@@ -30,6 +30,15 @@ class StandInCRF(torch.nn.Module):
         return self.weight * (-(segmentations * a_s).sum().view(1) / n)
 
 
+class StandInCRFWithBatchSize(StandInCRF):
+    """The same stand-in with DenseCRFLoss's `batch_size=` extension (the loss divides by the global batch itself)."""
+    accepts_batch_size = True
+
+    def forward(self, images, segmentations, batch_size=None):
+        n = segmentations.shape[0] if batch_size is None else batch_size
+        return super().forward(images, segmentations) * (segmentations.shape[0] / n)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -60,9 +69,15 @@ def _worker(rank, world, port, n_total, out_dir):
         share = mod_async(images[lo:hi], seg_async, global_batch=n_total)
         share.backward()
         async_total = mod_async.global_loss().clone()
+        # a local loss that takes the global batch itself (DenseCRFLoss does): no multiply outside, same numbers
+        seg_bs = segs[lo:hi].clone().requires_grad_(True)
+        mod_bs = ShardedCRFLoss(StandInCRFWithBatchSize(weight=1e-3), reduction="global")
+        loss_bs = mod_bs(images[lo:hi], seg_bs, global_batch=n_total)
+        loss_bs.backward()
         torch.save({"loss": loss.detach(), "loss2": loss2.detach(), "grad": local_segs.grad, "lo": lo, "hi": hi,
                     "local": local_only.detach(), "share": share.detach(), "async_total": async_total,
-                    "async_grad": seg_async.grad}, os.path.join(out_dir, f"rank{rank}.pt"))
+                    "async_grad": seg_async.grad, "loss_bs": loss_bs.detach(), "grad_bs": seg_bs.grad},
+                   os.path.join(out_dir, f"rank{rank}.pt"))
         # all_reduce_scalar is the identity in the backward pass
         v = torch.tensor([float(rank + 1)], requires_grad=True)
         s = all_reduce_scalar(v * 2.0)
@@ -91,6 +106,8 @@ def test_sharded_loss_matches_single_process(tmp_path, n_total):
         # the asynchronous reduction: same reduced value, same gradient, and the shares add up to the loss
         assert torch.allclose(d["async_total"], ref.detach(), rtol=1e-6)
         assert torch.equal(d["async_grad"], d["grad"])
+        assert torch.allclose(d["loss_bs"], ref.detach(), rtol=1e-6)
+        assert torch.allclose(d["grad_bs"], d["grad"], rtol=1e-6, atol=1e-12)
     assert covered == list(range(n_total))
     shares = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))["share"] for r in range(world)]
     assert torch.allclose(sum(shares), ref.detach(), rtol=1e-6)
