@@ -1084,6 +1084,25 @@ __device__ __forceinline__ float seg_value(const float *z, int k, int P, const S
     return L ? __fdiv_rn(expf(v - st.zmax), st.sum) : v;
 }
 
+// Two classes (what TCAM trains with: fg / bg) with the softmax fused in: both probabilities of a pixel are formed
+// once and kept in registers -- two loads, two expf, two divisions instead of softmax_stat's two passes plus
+// seg_value's recomputation per use (six loads, four to six expf: expf is ~28 instructions, and the gradient kernel
+// spent 388 instructions per pixel this way).  Same operations in the same order as softmax_stat + seg_value, hence
+// the same bits.
+struct Prob2 {
+    float p0, p1;
+    __device__ __forceinline__ void load(const float *z, int P)
+    {
+        const float z0 = __ldg(z), z1 = __ldg(z + P);
+        const float zmax = fmaxf(fmaxf(-INFINITY, z0), z1);
+        const float e0 = expf(z0 - zmax), e1 = expf(z1 - zmax);
+        const float sum = (0.f + e0) + e1;
+        p0 = __fdiv_rn(e0, sum);
+        p1 = __fdiv_rn(e1, sum);
+    }
+    __device__ __forceinline__ float get(int k) const { return k == 0 ? p0 : p1; }
+};
+
 template <int D, int V, bool L>
 __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
 {
@@ -1123,7 +1142,14 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     }
     const float *seg = p.segs + (size_t)n * p.K * p.P + (valid ? pix : 0);
     SoftmaxStat sm = {0.f, 1.f};
-    if (L && valid) sm = softmax_stat(seg, p.K, p.P);
+    Prob2 p2 = {0.f, 0.f};
+    const bool two = L && p.K == 2;
+    if (L && valid) {
+        if (two)
+            p2.load(seg, p.P);
+        else
+            sm = softmax_stat(seg, p.K, p.P);
+    }
     pdl_wait();   // the value rows are cleared by the previous kernel
     pdl_launch_dependents();
 #pragma unroll
@@ -1138,7 +1164,8 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const PixelParams p)
     for (int k = 0; k < p.Kp; k += V) {
         float s[V];
 #pragma unroll
-        for (int e = 0; e < V; e++) s[e] = (valid && k + e < p.K) ? seg_value<L>(seg, k + e, p.P, sm) : 0.f;
+        for (int e = 0; e < V; e++)
+            s[e] = (valid && k + e < p.K) ? ((L && two) ? p2.get(k + e) : seg_value<L>(seg, k + e, p.P, sm)) : 0.f;
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             float t[V];
@@ -1409,6 +1436,8 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
     float w[D + 1];
     const float *seg = p.segs + (size_t)n * p.K * p.P + pix;
     SoftmaxStat sm = {0.f, 1.f};
+    Prob2 p2 = {0.f, 0.f};
+    const bool two = L && p.K == 2;
     // ahead of the wait: vertex ids (splat), weights (build) and segmentations (caller) are all older than
     // the previous launch (the last blur pass)
     if (pix < p.P) {
@@ -1420,7 +1449,12 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
             // (bary * alpha) first, then * value (permutohedral.cpp:562-564)
             w[r] = __fmul_rn(p.bary[base + (size_t)r * p.P], p.alpha);
         }
-        if (L) sm = softmax_stat(seg, p.K, p.P);
+        if (L) {
+            if (two)
+                p2.load(seg, p.P);
+            else
+                sm = softmax_stat(seg, p.K, p.P);
+        }
     }
     pdl_wait();
     pdl_launch_dependents();
@@ -1448,7 +1482,7 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const PixelParams p)
                 if (k + e < p.K) {
                     const float o = poisoned ? __int_as_float(0x7fc00000) : acc[e];
                     out[(size_t)(k + e) * p.P] = o;
-                    dot = fmaf(seg_value<L>(seg, k + e, p.P, sm), o, dot);
+                    dot = fmaf((L && two) ? p2.get(k + e) : seg_value<L>(seg, k + e, p.P, sm), o, dot);
                 }
             }
         }
@@ -1507,10 +1541,21 @@ __global__ void __launch_bounds__(kThreads) loss_backward_logits_kernel(const fl
     const float t = __fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight));
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < pixels; i += stride) {
-        const long long n = i / P;
+        // (32-bit division when the pixel index fits: a 64-bit one is ~25 instructions more per pixel)
+        const long long n = pixels <= 0x7fffffffll ? (long long)((unsigned int)i / (unsigned int)P) : i / P;
         const size_t base = (size_t)n * K * P + (i - n * P);
         const float *z = logits + base;
         const float *a = as + base;
+        if (K == 2) {   // fg / bg: everything loaded once, the four loads in flight together
+            const float a0 = __ldg(a), a1 = __ldg(a + P);
+            Prob2 p2;
+            p2.load(z, P);
+            const float g0 = __fdiv_rn(__fmul_rn(t, a0), n_norm), g1 = __fdiv_rn(__fmul_rn(t, a1), n_norm);
+            const float inner2 = fmaf(p2.p1, g1, fmaf(p2.p0, g0, 0.f));
+            grad[base] = p2.p0 * (g0 - inner2);
+            grad[base + P] = p2.p1 * (g1 - inner2);
+            continue;
+        }
         const SoftmaxStat sm = softmax_stat(z, K, P);
         float inner = 0.f;
         for (int k = 0; k < K; k++) {
