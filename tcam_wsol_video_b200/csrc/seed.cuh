@@ -438,7 +438,11 @@ __global__ void __launch_bounds__(kSeedThreads) seed_select_smem_kernel(const Se
 namespace cg = cooperative_groups;
 
 constexpr int kSeedCluster = 8;          // portable cluster size
-constexpr int kSeedFusedThreads = 512;
+#ifndef TCAMCRF_SEED_THREADS
+#define TCAMCRF_SEED_THREADS 512
+#endif
+constexpr int kSeedFusedThreads = TCAMCRF_SEED_THREADS;   // 512 or 1024
+static_assert(kSeedFusedThreads >= 512 && kSeedFusedThreads <= 1024 && kSeedFusedThreads % 32 == 0, "one thread per (side, bin)");
 constexpr int kSeedFusedMaxK = 32;       // seeds per side this kernel handles (larger k: the two-kernel path)
 
 struct SeedFusedParams {
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(kSeedFusedThreads) seed_fused_kernel(const See
                 }
             }
             cluster.sync();   // every block's histogram of this pass is complete
-            {   // thread (side, bin): the bin summed over the cluster
+            if (tid < 512) {   // thread (side, bin): the bin summed over the cluster
                 const int side = tid >> 8, bin = tid & 255;
                 int sum = 0;
                 for (int r = 0; r < kSeedCluster; r++) sum += *cluster.map_shared_rank(&s_hist[hb][side][bin], r);
@@ -865,24 +869,52 @@ __global__ void __launch_bounds__(kSeedFusedThreads) seed_fused_kernel(const See
             p.sel[((size_t)b * 2 + side) * p.kmax + j] = j < kSeedFusedMaxK ? s_sel[side][j] : -1;
         }
     if (p.labels) {
-        // kornia 0.6.4 dilation with a flat ksz x ksz kernel (see seed_labels_kernel)
+        // kornia 0.6.4 dilation with a flat ksz x ksz kernel (see seed_labels_kernel).  The windows of the seeds are
+        // worked out once per block (rows / columns a seed reaches); a pixel then only compares.
+        __shared__ short s_win[2][kSeedFusedMaxK][4];   // y0, y1, x0, x1 (inclusive); y0 > y1: unused
         const int origin = p.ksz / 2, back = p.ksz - 1 - origin;
-        long long *out = p.labels + (size_t)b * HW;
         const int kk = min(p.kmax, kSeedFusedMaxK);
-        for (int i = lo + tid; i < hi; i += kSeedFusedThreads) {
-            const int y = i / p.W, x = i - y * p.W;
-            bool near[2] = {false, false};
-#pragma unroll
-            for (int c = 0; c < 2; c++)
-                for (int j = 0; j < kk; j++) {
-                    const int sp = s_sel[c][j];
-                    if (sp < 0) break;
-                    const int sy = sp / p.W, sx = sp - sy * p.W;
-                    if (y >= sy - back && y <= sy + origin && x >= sx - back && x <= sx + origin) near[c] = true;
+        for (int i = tid; i < 2 * kSeedFusedMaxK; i += kSeedFusedThreads) {
+            const int c = i / kSeedFusedMaxK, j = i - c * kSeedFusedMaxK;
+            const int sp = j < kk ? s_sel[c][j] : -1;
+            const int sy = sp >= 0 ? sp / p.W : 0, sx = sp >= 0 ? sp - sy * p.W : 0;
+            s_win[c][j][0] = (short)(sp >= 0 ? max(sy - back, -1) : 1);
+            s_win[c][j][1] = (short)(sp >= 0 ? min(sy + origin, 32766) : 0);
+            s_win[c][j][2] = (short)max(sx - back, -1);
+            s_win[c][j][3] = (short)min(sx + origin, 32766);
+        }
+        __syncthreads();
+        // rows of the frame any window reaches: outside them (nearly everywhere) a pixel is ignore without a look
+        int ymin = 0x7fffffff, ymax = -1;
+        for (int c = 0; c < 2; c++)
+            for (int j = 0; j < kk; j++)
+                if (s_win[c][j][0] <= s_win[c][j][1]) {
+                    ymin = min(ymin, (int)s_win[c][j][0]);
+                    ymax = max(ymax, (int)s_win[c][j][1]);
                 }
+        long long *out = p.labels + (size_t)b * HW;
+        int y = (lo + tid) / p.W, x = (lo + tid) - y * p.W;
+        const int dy = kSeedFusedThreads / p.W, dx = kSeedFusedThreads - dy * p.W;   // one division per thread, not per pixel
+        for (int i = lo + tid; i < hi; i += kSeedFusedThreads) {
+            bool near[2] = {false, false};
+            if (y >= ymin && y <= ymax) {
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+                    for (int j = 0; j < kk; j++) {
+                        if (s_win[c][j][0] > s_win[c][j][1]) break;   // seeds are filled from slot 0 on
+                        if (y >= s_win[c][j][0] && y <= s_win[c][j][1] && x >= s_win[c][j][2] && x <= s_win[c][j][3])
+                            near[c] = true;
+                    }
+            }
             long long label = p.ignore_idx;
             if (near[0] != near[1]) label = near[0] ? 1 : 0;   // claimed by both -> neither (tcam_seeding.py:247-250)
             out[i] = label;
+            y += dy;
+            x += dx;
+            if (x >= p.W) {
+                x -= p.W;
+                y++;
+            }
         }
     }
 }
