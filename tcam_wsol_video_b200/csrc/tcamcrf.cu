@@ -452,6 +452,9 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(Entry *table, int *ct
 #ifndef TCAMCRF_BUILD_MINBLOCKS
 #define TCAMCRF_BUILD_MINBLOCKS 5
 #endif
+#ifndef TCAMCRF_BUILD_CAS_BATCH
+#define TCAMCRF_BUILD_CAS_BATCH 1
+#endif
 // Front end shared by the two build kernels: the pixel's features (initializePermutohedral, bilateralfilter.cpp:4-19 /
 // colorbilateralfilter.cpp:4-15), its embedding, the d+1 packed keys of its simplex, and the barycentric weights,
 // which leave the registers right here.  Reads the caller's images only, so it runs ahead of griddepcontrol.wait (the
@@ -573,6 +576,34 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
     constexpr int kLockstepRounds = 6;
     int rounds = 0;
     for (; rounds < kLockstepRounds && pend; rounds++) {
+#if TCAMCRF_BUILD_CAS_BATCH
+        // every claim of the round is issued before any result is looked at: with the compare-and-swap and the test of
+        // its result in one branch per key, a warp went through up to d+1 atomic round trips one after the other
+        unsigned int tried = 0;
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            if ((pend & (1u << r)) && cur[r] == kEmptyKey) {
+                tried |= 1u << r;
+                cur[r] = atomicCAS(&tab[slot[r]].key, kEmptyKey, key[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            if (!(pend & (1u << r))) continue;
+            unsigned long long c = cur[r];
+            if (tried & (1u << r)) {
+                vid[r] = -1;   // ours to allocate below, or created this instant by another thread
+                if (c == kEmptyKey) {
+                    wonmask |= 1u << r;
+                    c = key[r];
+                }
+            }
+            if (c == key[r])
+                pend &= ~(1u << r);
+            else
+                slot[r] = (int)(((unsigned int)slot[r] + 1u) & mask1);
+        }
+#else
 #pragma unroll
         for (int r = 0; r <= D; r++) {
             if (!(pend & (1u << r))) continue;
@@ -590,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, TCAMCRF_BUILD_MINBLOCKS) build_kerne
             else
                 slot[r] = (int)(((unsigned int)slot[r] + 1u) & mask1);
         }
+#endif
 #pragma unroll
         for (int r = 0; r <= D; r++)
             if (pend & (1u << r)) load_entry_cg(tab + slot[r], cur[r], vid[r]);
